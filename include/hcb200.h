@@ -1,0 +1,102 @@
+/* hcb200.h — C ABI of the B200-native homotopy-continuation path tracker for trifocal_2op1p_30x30.
+ *
+ * This is the drop-in boundary: the entry points below replace the reference's kernel launch wrappers
+ *
+ *   kernel_GPUHC_trifocal_2op1p_30x30_PH_CodeOpt_TrunPaths            magmaHC/gpu-kernels/magmaHC-kernels.hpp:24-39
+ *   kernel_GPUHC_trifocal_2op1p_30x30_PH_CodeOpt_TrunPaths_TrunRANSAC magmaHC/gpu-kernels/magmaHC-kernels.hpp:61-81
+ *
+ * (called from GPU_HC_Solver::Solve_by_GPU_HC, magmaHC/GPU_HC_Solver.cpp:395-433).  Conventions kept from the
+ * reference: the CALLER owns every buffer; the current CUDA device is the caller's; work is ENQUEUED on `stream`
+ * and the call returns immediately (the caller synchronises, GPU_HC_Solver.cpp:440-444).  Differences: plain C
+ * types (cudaStream_t as void*, float2 as float[2]), an int (cudaError_t) status instead of a dummy time, and no
+ * MAGMA queue / pointer arrays / index table (the polynomial system is compiled into the library).
+ * INTEGRATION.md shows the ten-line shim that gives the reference's exact C++ signatures on top of this ABI.
+ *
+ * Layouts (reference: SURVEY.md App. A.5)
+ *   start_sols    [312][31] complex64   start solutions, entry 30 == 1+0i        (d_Start_Sols,  Data_Reader.cpp:37-60)
+ *   start_params  [34]      complex64   entry 33 == 1+0i                          (d_Start_Params)
+ *   target_params [n_hyp][34] complex64 per RANSAC hypothesis                     (d_Target_Params, GPU_HC_Solver.cpp:276-292)
+ *   diff_params   [n_hyp][34] complex64 target - start                            (d_diffParams,  GPU_HC_Solver.cpp:295-296)
+ *   tracks        [n_hyp*312][31] complex64  OUT: end point of every path (need not be pre-loaded with the start
+ *                                        solutions — the reference requires that, GPU_HC_Solver.cpp:208,342)
+ *   converged / infinity [n_hyp*312] uint8 (C++ bool)  OUT                        (d_is_GPU_HC_Sol_Converge / _Infinity)
+ *   path id = hypothesis*312 + start-solution index                              (…TrunPaths.cu:67-69)
+ */
+#ifndef HCB200_H
+#define HCB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HCB200_NUM_VARS 30
+#define HCB200_NUM_PARAMS 33
+#define HCB200_NUM_TRACKS 312
+#define HCB200_ABI_VERSION 1
+
+/* flags */
+#define HCB200_FLAG_PRUNE_PATHS 1u   /* positive-depth path pruning (always on in the reference GPU kernels, …TrunPaths.cu:148-154) */
+
+/* Optional per-path counters (all int32): HC steps attempted, predictor stages, corrector stages,
+ * rejected steps | end reason << 16 (0 converged, 1 infinity, 2 pruned, 3 step cap, 4 skipped after abort). */
+typedef struct { int32_t steps, pred_stages, corr_stages, rejected_reason; } hcb200_path_stats;
+
+/* Best candidate of an early-abort launch, reduced on the device (64 bytes). */
+typedef struct {
+  int32_t found;            /* 0/1: some path passed the inlier test                                   */
+  int32_t path_id;          /* smallest passing path id of this launch (hypothesis*312 + track), or -1 */
+  int32_t inliers21, inliers31;   /* its reprojection inlier counts (views 1-2, 1-3)                   */
+  int32_t n_passed;         /* number of paths that passed before the launch drained                   */
+  int32_t reserved[11];
+} hcb200_best_record;
+
+/* Device workspace the launches need (work counter + reduction scratch); zeroing is done by the launch itself. */
+size_t hcb200_workspace_bytes(void);
+int hcb200_abi_version(void);
+
+/* Replaces kernel_GPUHC_trifocal_2op1p_30x30_PH_CodeOpt_TrunPaths (…TrunPaths.cu:292-386).
+ * Tracks all 312*n_hyp paths in one launch.  `stats` may be NULL.  Returns a cudaError_t value (0 == success). */
+int hcb200_track(void* stream, int n_hyp,
+                 int hc_max_steps, int hc_max_correction_steps, int hc_delta_t_incremental_steps, unsigned flags,
+                 const float* d_start_sols, const float* d_start_params,
+                 const float* d_target_params, const float* d_diff_params,
+                 float* d_tracks, uint8_t* d_converged, uint8_t* d_infinity,
+                 hcb200_path_stats* d_stats, void* d_workspace);
+
+/* Replaces kernel_GPUHC_trifocal_2op1p_30x30_PH_CodeOpt_TrunPaths_TrunRANSAC (…TrunRANSAC.cu:329-453): as above plus
+ * in-kernel scoring of every converged path against all edgel triplets and a device-side abort flag.
+ *   d_edgel_locations [n_edgels][6] float32  (x1 y1 x2 y2 x3 y3, normalised coordinates)   (d_Triplet_Edge_Locations)
+ *   d_intrinsic       [9] float32 row-major K                                             (d_Intrinsic_Matrix)
+ *   d_found           [1] uint8 in/out: must be 0 on entry; set to 1 by the first passing path (d_Found_Trifocal_Sols)
+ *   d_found_index     [n_hyp*312] int32 in/out: pre-set to -1 by the caller, entry b becomes b if path b passed
+ *                                                                                          (d_Trifocal_Sols_Batch_Index)
+ *   d_best            optional (may be NULL) hcb200_best_record, written when the launch drains.
+ * Paths that start after the flag is up are skipped (converged = 0, end point = start solution) like the reference;
+ * unlike the reference the flag is also polled at every HC step, and the infinity flag of skipped paths is 0. */
+int hcb200_track_abort(void* stream, int n_hyp, int n_edgels,
+                       int hc_max_steps, int hc_max_correction_steps, int hc_delta_t_incremental_steps, unsigned flags,
+                       const float* d_start_sols, const float* d_start_params,
+                       const float* d_target_params, const float* d_diff_params,
+                       const float* d_edgel_locations, const float* d_intrinsic,
+                       float* d_tracks, uint8_t* d_converged, uint8_t* d_infinity,
+                       uint8_t* d_found, int32_t* d_found_index, hcb200_best_record* d_best,
+                       hcb200_path_stats* d_stats, void* d_workspace);
+
+/* Device-side hypothesis generation (Prepare_Target_Params at scale, GPU_HC_Solver.cpp:252-306): given the picked
+ * edgel indices [n_hyp][3] it gathers the 34 target parameters and target - start for every hypothesis. */
+int hcb200_build_target_params(void* stream, int n_hyp, const int32_t* d_picked, int n_edgels,
+                               const float* d_edgel_locations, const float* d_edgel_tangents,
+                               const float* d_start_params, float* d_target_params, float* d_diff_params);
+
+/* Introspection for benchmarks/tests: registers per thread, static+dynamic shared bytes per CTA, resident CTAs per SM,
+ * grid size a launch would use on the current device.  Any pointer may be NULL. */
+int hcb200_kernel_info(int abort_variant, int* regs, int* smem_bytes, int* ctas_per_sm, int* grid, int* block);
+
+const char* hcb200_error_string(int code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,499 @@
+/* hc_oracle.c — see hc_oracle.h.  TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Build: gcc -std=c11 -O2 -ffp-contract=off -fno-fast-math -fopenmp -fPIC -shared hc_oracle.c -lm
+ * -ffp-contract=off matters: every fused multiply-add below is an explicit fmaf(), every other operation is
+ * individually rounded (IEEE-754 binary32, round to nearest even, denormals kept) — the same contract the CUDA
+ * kernels are compiled under (-fmad=false + explicit fmaf, -prec-div=true, -prec-sqrt=true, -ftz=false).
+ */
+#include "hc_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------
+ * complex helpers (the arithmetic spec)
+ * MAGMA's operator* is (ar*br - ai*bi, ai*br + ar*bi); the spec fixes where the single FMA sits. */
+static inline hco_c32 c_make(float re, float im) { hco_c32 z; z.re = re; z.im = im; return z; }
+static inline hco_c32 c_mul(hco_c32 a, hco_c32 b)
+{ return c_make(fmaf(a.re, b.re, -(a.im * b.im)), fmaf(a.re, b.im, a.im * b.re)); }
+static inline hco_c32 c_add(hco_c32 a, hco_c32 b) { return c_make(a.re + b.re, a.im + b.im); }
+static inline hco_c32 c_sub(hco_c32 a, hco_c32 b) { return c_make(a.re - b.re, a.im - b.im); }
+static inline hco_c32 c_scale(float s, hco_c32 a) { return c_make(s * a.re, s * a.im); }
+/* acc - m*u, four dependent FMAs */
+static inline hco_c32 c_msub(hco_c32 acc, hco_c32 m, hco_c32 u)
+{
+  float re = fmaf(-m.re, u.re, acc.re); re = fmaf(m.im, u.im, re);
+  float im = fmaf(-m.re, u.im, acc.im); im = fmaf(-m.im, u.re, im);
+  return c_make(re, im);
+}
+/* 1/z with the scaling of cuCdivf (MAGMA_C_DIV, dev-cgesv-batched-small.cuh:84) */
+static inline hco_c32 c_recip(hco_c32 z)
+{
+  float s = fabsf(z.re) + fabsf(z.im);
+  float oos = 1.0f / s;
+  float a = z.re * oos, b = z.im * oos;
+  float d = fmaf(a, a, b * b);
+  float q = 1.0f / d;
+  float t = oos * q;
+  return c_make(a * t, -(b * t));
+}
+static inline uint32_t f_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * evaluators — literal restatement of cpu-eval-indx_trifocal_2op1p_30x30.hpp:22-89: every factor position is
+ * multiplied, padded ones (p[33] == 1, x[30] == 1) included, left to right, terms added in table order.
+ * Table index: Hx (col*40 + term*5 + part)*30 + row ; Ht/H (term*6 + part)*30 + row  (SURVEY.md App. A.3). */
+void hco_param_homotopy(float t, const hco_c32* start34, const hco_c32* target34, hco_c32* p34)
+{
+  /* CPU_HC_Solver.hpp:102-106 / …L2Cache.cuh:40-54: target*t + start*(1.0-t); (1.0-t) rounds once to float */
+  float omt = 1.0f - t;
+  for (int i = 0; i < HCO_NP; i++) {
+    p34[i].re = fmaf(target34[i].re, t, start34[i].re * omt);
+    p34[i].im = fmaf(target34[i].im, t, start34[i].im * omt);
+  }
+  p34[HCO_NP] = c_make(1.0f, 0.0f);
+}
+
+static inline hco_c32 coef_pp(int coef, hco_c32 pa, hco_c32 pb)   /* coef * p[a] * p[b] */
+{ return c_scale((float)coef, c_mul(pa, pb)); }
+
+void hco_eval_Hx(const int* dHdx, const hco_c32* x, const hco_c32* p, hco_c32* A)
+{
+  for (int row = 0; row < HCO_N; row++)
+    for (int col = 0; col < HCO_N; col++) {
+      hco_c32 acc = c_make(0.0f, 0.0f);
+      for (int j = 0; j < HCO_HX_TERMS; j++) {
+        const int base = (col * HCO_HX_TERMS * HCO_HX_PARTS + j * HCO_HX_PARTS) * HCO_N + row;
+        int coef = dHdx[base];
+        if (coef == 0) continue;                               /* adds an exact +0 in the reference */
+        hco_c32 t = coef_pp(coef, p[dHdx[base + 1 * HCO_N]], p[dHdx[base + 2 * HCO_N]]);
+        t = c_mul(t, x[dHdx[base + 3 * HCO_N]]);
+        t = c_mul(t, x[dHdx[base + 4 * HCO_N]]);
+        acc = c_add(acc, t);
+      }
+      A[row * HCO_N + col] = acc;
+    }
+}
+
+void hco_eval_H(const int* dHdt, const hco_c32* x, const hco_c32* p, hco_c32* b)
+{
+  for (int row = 0; row < HCO_N; row++) {
+    hco_c32 acc = c_make(0.0f, 0.0f);
+    for (int j = 0; j < HCO_HT_TERMS; j++) {
+      const int base = (j * HCO_HT_PARTS) * HCO_N + row;
+      int coef = dHdt[base];
+      if (coef == 0) continue;
+      hco_c32 t = coef_pp(coef, p[dHdt[base + 1 * HCO_N]], p[dHdt[base + 2 * HCO_N]]);
+      t = c_mul(t, x[dHdt[base + 3 * HCO_N]]);
+      t = c_mul(t, x[dHdt[base + 4 * HCO_N]]);
+      t = c_mul(t, x[dHdt[base + 5 * HCO_N]]);
+      acc = c_add(acc, t);
+    }
+    b[row] = acc;
+  }
+}
+
+void hco_eval_Ht(const int* dHdt, const hco_c32* x, const hco_c32* p, const hco_c32* dp, hco_c32* b)
+{
+  for (int row = 0; row < HCO_N; row++) {
+    hco_c32 acc = c_make(0.0f, 0.0f);
+    for (int j = 0; j < HCO_HT_TERMS; j++) {
+      const int base = (j * HCO_HT_PARTS) * HCO_N + row;
+      int coef = dHdt[base];
+      int ia = dHdt[base + 1 * HCO_N], ib = dHdt[base + 2 * HCO_N];
+      if (coef == 0) continue;
+      if (ia == HCO_NP && ib == HCO_NP) continue;              /* dp[33] == 0: the term is an exact 0 */
+      hco_c32 s = c_add(c_mul(dp[ia], p[ib]), c_mul(dp[ib], p[ia]));
+      hco_c32 t = c_scale((float)coef, s);
+      t = c_mul(t, x[dHdt[base + 3 * HCO_N]]);
+      t = c_mul(t, x[dHdt[base + 4 * HCO_N]]);
+      t = c_mul(t, x[dHdt[base + 5 * HCO_N]]);
+      acc = c_sub(acc, t);                                     /* r_cgesvB -= … (…L2Cache.cuh:110) */
+    }
+    b[row] = acc;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * linear solve — the spec.
+ * Same pivot rule as dev-cgesv-batched-small.cuh:55-81 (key |re|+|im|, first maximum in CURRENT row order wins,
+ * virtual row exchange through `pos`), same multipliers (row entry times the pivot's reciprocal, :84-86) and the
+ * same rank-1 updates (:87-93).  The only re-organisation: rows that were already pivoted are swept too
+ * (Gauss-Jordan), which performs the U-solve (:97-106) inside the same 30 steps; x_k = b_pivot(k) * (1/pivot_k). */
+int hco_solve(hco_c32* A, hco_c32* b)
+{
+  int pos[HCO_N], done[HCO_N], piv[HCO_N], info = 0;
+  hco_c32 rsave[HCO_N];
+  for (int i = 0; i < HCO_N; i++) { pos[i] = i; done[i] = 0; }
+  for (int k = 0; k < HCO_N; k++) {
+    uint32_t maxbits = 0;
+    uint32_t key[HCO_N];
+    for (int i = 0; i < HCO_N; i++) {
+      key[i] = done[i] ? 0u : f_bits(fabsf(A[i * HCO_N + k].re) + fabsf(A[i * HCO_N + k].im));
+      if (key[i] > maxbits) maxbits = key[i];
+    }
+    int p = -1, ppos = 1 << 30, q = -1;
+    for (int i = 0; i < HCO_N; i++) {
+      if (!done[i] && key[i] == maxbits && pos[i] < ppos) { p = i; ppos = pos[i]; }
+      if (pos[i] == k) q = i;
+    }
+    pos[q] = pos[p]; pos[p] = k; done[p] = 1; piv[k] = p;
+    if (maxbits == 0 && info == 0) info = k + 1;
+    const hco_c32 r = c_recip(A[p * HCO_N + k]);
+    rsave[p] = r;
+    for (int i = 0; i < HCO_N; i++) {
+      if (i == p) continue;
+      const hco_c32 m = c_mul(A[i * HCO_N + k], r);
+      for (int j = k + 1; j < HCO_N; j++)
+        A[i * HCO_N + j] = c_msub(A[i * HCO_N + j], m, A[p * HCO_N + j]);
+      b[i] = c_msub(b[i], m, b[p]);
+    }
+  }
+  hco_c32 x[HCO_N];
+  for (int k = 0; k < HCO_N; k++) x[k] = c_mul(b[piv[k]], rsave[piv[k]]);
+  memcpy(b, x, sizeof x);
+  return info;
+}
+
+/* Literal operation order of cgesv_batched_small_device<30> (dev-cgesv-batched-small.cuh:38-107), kept to show that
+ * the spec above solves the same systems to rounding (tests/test_oracle.py).  cuCdivf is restated from cuComplex.h. */
+static inline hco_c32 c_div_cu(hco_c32 x, hco_c32 y)
+{
+  float s = fabsf(y.re) + fabsf(y.im);
+  float oos = 1.0f / s;
+  float ars = x.re * oos, ais = x.im * oos, brs = y.re * oos, bis = y.im * oos;
+  s = (brs * brs) + (bis * bis);
+  oos = 1.0f / s;
+  return c_make(((ars * brs) + (ais * bis)) * oos, ((ais * brs) - (ars * bis)) * oos);
+}
+static inline hco_c32 c_mul_plain(hco_c32 a, hco_c32 b)
+{ return c_make(a.re * b.re - a.im * b.im, a.im * b.re + a.re * b.im); }
+
+int hco_solve_lu_ref(hco_c32* A, hco_c32* b)
+{
+  int rowid[HCO_N], info = 0;
+  hco_c32 sx[HCO_N], sB[HCO_N];
+  float dsx[HCO_N];
+  for (int i = 0; i < HCO_N; i++) rowid[i] = i;
+  for (int i = 0; i < HCO_N; i++) {
+    for (int t = 0; t < HCO_N; t++) dsx[rowid[t]] = fabsf(A[t * HCO_N + i].re) + fabsf(A[t * HCO_N + i].im);
+    float mx = dsx[i]; int max_id = i;
+    for (int j = i + 1; j < HCO_N; j++) if (dsx[j] > mx) { max_id = j; mx = dsx[j]; }
+    int zero = (mx == 0.0f);
+    if (zero && !info) info = i + 1;
+    float update = zero ? 0.0f : 1.0f;
+    hco_c32 sB0 = c_make(0, 0);
+    for (int t = 0; t < HCO_N; t++) {
+      if (rowid[t] == max_id) {
+        rowid[t] = i;
+        for (int j = i; j < HCO_N; j++) sx[j] = c_scale(update, A[t * HCO_N + j]);
+        sB0 = b[t];
+      } else if (rowid[t] == i) rowid[t] = max_id;
+    }
+    hco_c32 reg = zero ? c_make(1, 0) : c_div_cu(c_make(1, 0), sx[i]);
+    for (int t = 0; t < HCO_N; t++) {
+      if (rowid[t] > i) {
+        A[t * HCO_N + i] = c_mul_plain(A[t * HCO_N + i], reg);
+        for (int j = i + 1; j < HCO_N; j++)
+          A[t * HCO_N + j] = c_sub(A[t * HCO_N + j], c_mul_plain(A[t * HCO_N + i], sx[j]));
+        b[t] = c_sub(b[t], c_mul_plain(A[t * HCO_N + i], sB0));
+      }
+    }
+  }
+  for (int t = 0; t < HCO_N; t++) sB[rowid[t]] = b[t];
+  for (int i = HCO_N - 1; i >= 0; i--) {
+    for (int t = 0; t < HCO_N; t++) sx[rowid[t]] = A[t * HCO_N + i];
+    hco_c32 reg = c_div_cu(sB[i], sx[i]);
+    for (int t = 0; t < i; t++) sB[t] = c_sub(sB[t], c_mul_plain(reg, sx[t]));
+    sB[i] = reg;
+  }
+  memcpy(b, sB, sizeof sB);
+  return info;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * warp-order sum of 30 per-row values (the kernel adds lanes 30,31 as zeros in an xor butterfly 16,8,4,2,1;
+ * the reference's shuffle-down tree is …TrunPaths.cu:236-239) */
+static float butterfly_sum(const float* v30)
+{
+  float v[32];
+  for (int i = 0; i < 32; i++) v[i] = i < HCO_N ? v30[i] : 0.0f;
+  for (int off = 16; off > 0; off >>= 1) {
+    float w[32];
+    for (int i = 0; i < 32; i++) w[i] = v[i] + v[i ^ off];
+    memcpy(v, w, sizeof v);
+  }
+  return v[0];
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * one path: …TrunPaths.cu:80-286, cfg->prune == 0 gives CPUHC_Generic_Solver_Eval_by_Indx.cpp:67-172 */
+void hco_track_path(const int* dHdx, const int* dHdt, const hco_c32* start_sol31, const hco_c32* sp,
+                    const hco_c32* tp, const hco_c32* dp, const hco_settings* cfg,
+                    hco_c32* out_track31, uint8_t* out_conv, uint8_t* out_inf, hco_path_stats* st)
+{
+  hco_c32 x[HCO_N + 1], last[HCO_N], sols[HCO_N], p[HCO_NP + 1], A[HCO_N * HCO_N], b[HCO_N];
+  for (int i = 0; i < HCO_N; i++) x[i] = last[i] = sols[i] = start_sol31[i];
+  x[HCO_N] = c_make(1.0f, 0.0f);
+  float t0 = 0.0f, t_step = 0.0f, delta_t = 0.01f;
+  int end_zone = 0, counter = 0, ok = 0, inf_fail = 0, check_depths = 1;
+  hco_path_stats s = {0, 0, 0, 0, 3};
+  static const float c6[3] = {(float)(1.0 / 6.0), (float)(2.0 / 6.0), (float)(2.0 / 6.0)};   /* …TrunPaths.cu:193 */
+
+  for (int step = 0; step <= cfg->max_steps; step++) {
+    if (!((double)t0 < 1.0 && (1.0 - (double)t0 > 0.0000001))) { s.end_reason = 0; break; }        /* :139 */
+    if (!end_zone && (double)fabsf(1.0f - t0) <= 0.0500001) end_zone = 1;                            /* :144-146 */
+    if (cfg->prune) {                                                                               /* :148-154 */
+      if (check_depths) {
+        int all_pos = 1;
+        for (int i = 0; i < 8; i++) all_pos &= (x[i].re > 0.0f);
+        if (t0 > 0.0f) check_depths = all_pos ? 0 : 1;
+      }
+      if ((double)t0 > 0.95 && check_depths) { s.end_reason = 2; break; }
+    }
+    if (end_zone) { float r = fabsf(1.0f - t0); if (delta_t > r) delta_t = r; }                      /* :156-162 */
+    else { double r = fabs(0.95 - (double)t0); if ((double)delta_t > r) delta_t = (float)r; }
+    t_step = t0;
+    const float half = 0.5f * delta_t;
+    s.steps++;
+
+    /* RK4 predictor, "loopy" form (:170-211) */
+    for (int r = 0; r < 4; r++) {
+      hco_param_homotopy(t0, sp, tp, p);
+      hco_eval_Hx(dHdx, x, p, A);
+      hco_eval_Ht(dHdt, x, p, dp, b);
+      hco_solve(A, b);
+      s.pred_stages++;
+      if (r < 3) {
+        const float sc = (r < 2) ? half : delta_t;
+        for (int i = 0; i < HCO_N; i++) {
+          sols[i].re = fmaf(b[i].re * delta_t, c6[r], sols[i].re);
+          sols[i].im = fmaf(b[i].im * delta_t, c6[r], sols[i].im);
+          x[i].re = fmaf(b[i].re, sc, last[i].re);
+          x[i].im = fmaf(b[i].im, sc, last[i].im);
+        }
+        if (r != 1) t0 += half;
+      } else {
+        for (int i = 0; i < HCO_N; i++) {
+          sols[i].re = fmaf(b[i].re * delta_t, c6[0], sols[i].re);
+          sols[i].im = fmaf(b[i].im * delta_t, c6[0], sols[i].im);
+          x[i] = sols[i];
+        }
+      }
+    }
+
+    /* Newton corrector (:216-250); the parameter homotopy is NOT re-evaluated */
+    for (int c = 0; c < cfg->max_corr_steps; c++) {
+      hco_eval_Hx(dHdx, x, p, A);
+      hco_eval_H(dHdt, x, p, b);
+      hco_solve(A, b);
+      s.corr_stages++;
+      float vd[HCO_N], vx[HCO_N];
+      for (int i = 0; i < HCO_N; i++) {
+        x[i] = c_sub(x[i], b[i]);
+        vd[i] = fmaf(b[i].re, b[i].re, b[i].im * b[i].im);
+        vx[i] = fmaf(x[i].re, x[i].re, x[i].im * x[i].im);
+      }
+      const float sum_d = butterfly_sum(vd), sum_x = butterfly_sum(vx);
+      ok = (double)sum_d < 0.000001 * (double)sum_x;
+      inf_fail = (double)sum_x > 1e14;
+      if (inf_fail) break;
+      if (ok) break;
+    }
+    if (inf_fail) { s.end_reason = 1; break; }                                                       /* :252 */
+
+    if (!ok) {                                                                                      /* :257-275 */
+      delta_t *= 0.5f;
+      for (int i = 0; i < HCO_N; i++) x[i] = sols[i] = last[i];
+      counter = 0;
+      t0 = t_step;
+      s.rejected++;
+    } else {
+      counter++;
+      for (int i = 0; i < HCO_N; i++) last[i] = sols[i] = x[i];
+      if (counter >= cfg->dt_inc_steps) { counter = 0; delta_t *= 2.0f; }
+    }
+  }
+  const int conv = ((double)t0 >= 1.0 || (1.0 - (double)t0 <= 0.0000001));                           /* :284 */
+  if (conv && s.end_reason == 3) s.end_reason = 0;
+  memcpy(out_track31, x, sizeof(hco_c32) * (HCO_N + 1));
+  *out_conv = (uint8_t)conv;
+  *out_inf = (uint8_t)inf_fail;
+  if (st) *st = s;
+}
+
+void hco_track_batch(const int* dHdx, const int* dHdt, const hco_c32* start_sols, const hco_c32* sp,
+                     const hco_c32* target, const hco_c32* diff, int n_hyp, const hco_settings* cfg, int n_threads,
+                     hco_c32* tracks, uint8_t* converged, uint8_t* infinity, hco_path_stats* stats)
+{
+  const long n_paths = (long)n_hyp * HCO_TRACKS;
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+  #pragma omp parallel for schedule(dynamic, 4)
+  for (long ix = 0; ix < n_paths; ix++) {
+    const int h = (int)(ix / HCO_TRACKS), s = (int)(ix % HCO_TRACKS);
+    hco_track_path(dHdx, dHdt, start_sols + (size_t)s * (HCO_N + 1), sp, target + (size_t)h * (HCO_NP + 1),
+                   diff + (size_t)h * (HCO_NP + 1), cfg, tracks + (size_t)ix * (HCO_N + 1), converged + ix, infinity + ix,
+                   stats ? stats + ix : NULL);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * early-abort scoring: dev-trifocal_2op1p-eval.cuh:28-250 with a fixed FMA placement; rnorm3df -> 1/sqrtf,
+ * hypotf -> sqrtf (both correctly rounded here and, with -prec-sqrt/-prec-div, on the device). */
+static void cayley_to_R(const float r0, const float r1, const float r2, float* R)
+{
+  const float a00 = r0 * r0, a11 = r1 * r1, a22 = r2 * r2;
+  R[0] = (1.0f + a00) - (a11 + a22);
+  R[1] = 2.0f * fmaf(r0, r1, -r2);
+  R[2] = 2.0f * fmaf(r0, r2, r1);
+  R[3] = 2.0f * fmaf(r0, r1, r2);
+  R[4] = (1.0f + a11) - (a00 + a22);
+  R[5] = 2.0f * fmaf(r1, r2, -r0);
+  R[6] = 2.0f * fmaf(r0, r2, -r1);
+  R[7] = 2.0f * fmaf(r1, r2, r0);
+  R[8] = (1.0f + a22) - (a00 + a11);
+  /* :78-91 — column norms applied row-wise, exactly as the reference does */
+  const float n0 = 1.0f / sqrtf(fmaf(R[0], R[0], fmaf(R[3], R[3], R[6] * R[6])));
+  const float n1 = 1.0f / sqrtf(fmaf(R[1], R[1], fmaf(R[4], R[4], R[7] * R[7])));
+  const float n2 = 1.0f / sqrtf(fmaf(R[2], R[2], fmaf(R[5], R[5], R[8] * R[8])));
+  R[0] *= n0; R[1] *= n0; R[2] *= n0;
+  R[3] *= n1; R[4] *= n1; R[5] *= n1;
+  R[6] *= n2; R[7] *= n2; R[8] *= n2;
+}
+
+static inline int reproj_inlier(const float* R, const float* T, float g1x, float g1y, float gx, float gy,
+                                float B, float fx, float fy, float cx, float cy)
+{
+  const float A = fmaf(R[2], gx, fmaf(R[5], gy, R[8]));                    /* e3' R' gamma */
+  const float numer = fmaf(T[2], A, -B);
+  const float C = fmaf(R[6], g1x, fmaf(R[7], g1y, R[8]));                  /* e3' R gamma1 */
+  const float denom = fmaf(-C, A, 1.0f);
+  const float z = fmaf(numer, C, denom * T[2]);
+  const float X = fmaf(numer, fmaf(R[0], g1x, fmaf(R[1], g1y, R[2])), denom * T[0]) / z;
+  const float Y = fmaf(numer, fmaf(R[3], g1x, fmaf(R[4], g1y, R[5])), denom * T[1]) / z;
+  const float ex = fmaf(X, fx, cx) - fmaf(gx, fx, cx);
+  const float ey = fmaf(Y, fy, cy) - fmaf(gy, fy, cy);
+  return sqrtf(fmaf(ex, ex, ey * ey)) < 2.0f;                              /* REPROJ_ERROR_INLIER_THRESH */
+}
+
+int hco_score_solution(const hco_c32* x, const float* loc, int n_edgels, const float* K, int* n21, int* n31, int* gate_out)
+{
+  int gate = 1;
+  for (int i = 18; i < 30; i++) gate &= ((double)fabsf(x[i].im) < 1e-5);   /* IMAG_PART_TOL, :41-54 */
+  if (gate_out) *gate_out = gate;
+  *n21 = 0; *n31 = 0;
+  if (!gate) return 0;
+  float R21[9], R31[9], T21[3], T31[3];
+  cayley_to_R(x[24].re, x[25].re, x[26].re, R21);
+  cayley_to_R(x[27].re, x[28].re, x[29].re, R31);
+  for (int i = 0; i < 3; i++) { T21[i] = x[18 + i].re; T31[i] = x[21 + i].re; }
+  const float fx = K[0], fy = K[4], cx = K[3], cy = K[5];                  /* …TrunRANSAC.cu:138-141 (cx = K[3]) */
+  const float B21 = fmaf(R21[2], T21[0], fmaf(R21[5], T21[1], R21[8] * T21[2]));
+  const float B31 = fmaf(R31[2], T31[0], fmaf(R31[5], T31[1], R31[8] * T31[2]));
+  int c21 = 0, c31 = 0;
+  for (int e = 0; e < n_edgels; e++) {
+    const float* g = loc + (size_t)e * 6;
+    c21 += reproj_inlier(R21, T21, g[0], g[1], g[2], g[3], B21, fx, fy, cx, cy);
+    c31 += reproj_inlier(R31, T31, g[0], g[1], g[4], g[5], B31, fx, fy, cx, cy);
+  }
+  *n21 = c21; *n31 = c31;
+  const float r21 = (float)c21 / (float)n_edgels, r31 = (float)c31 / (float)n_edgels;
+  return ((double)r21 >= 0.90 && (double)r31 >= 0.90);                     /* PASS_RANSAC_INLIER_SUPPORT_RATIO, :241-242 */
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * GPU_HC_Solver.cpp:252-306 — one rand() stream, three draws per attempt, e0 != e1 and e1 != e2 accepted */
+void hco_prepare_target_params(unsigned seed, int n_hyp, int n_edgels, const float* loc, const float* tan,
+                               const hco_c32* sp, hco_c32* target, hco_c32* diff, int* picked)
+{
+  srand(seed);
+  for (int h = 0; h < n_hyp; h++) {
+    unsigned e[3];
+    for (;;) {
+      for (int r = 0; r < 3; r++) e[r] = (unsigned)rand() % (unsigned)n_edgels;
+      if (e[0] != e[1] && e[1] != e[2]) break;
+    }
+    hco_c32* T = target + (size_t)h * (HCO_NP + 1);
+    hco_c32* D = diff + (size_t)h * (HCO_NP + 1);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 6; j++) T[i * 6 + j] = c_make(loc[(size_t)e[i] * 6 + j], 0.0f);
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 6; j++) T[18 + i * 6 + j] = c_make(tan[(size_t)e[i] * 6 + j], 0.0f);
+    T[30] = c_make(1.0f, 0.0f); T[31] = c_make(0.5f, 0.0f); T[32] = c_make(1.0f, 0.0f); T[33] = c_make(1.0f, 0.0f);
+    for (int i = 0; i <= HCO_NP; i++) D[i] = c_sub(T[i], sp[i]);
+    if (picked) for (int r = 0; r < 3; r++) picked[h * 3 + r] = (int)e[r];
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * double-precision Newton polish against the target system (test helper) */
+typedef struct { double re, im; } zc;
+static inline zc z_mul(zc a, zc b) { zc r = {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; return r; }
+static inline zc z_sub(zc a, zc b) { zc r = {a.re - b.re, a.im - b.im}; return r; }
+static inline zc z_add(zc a, zc b) { zc r = {a.re + b.re, a.im + b.im}; return r; }
+static inline zc z_div(zc a, zc b)
+{ double d = b.re * b.re + b.im * b.im; zc r = {(a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d}; return r; }
+
+double hco_newton_refine_f64(const int* dHdx, const int* dHdt, const hco_c32* tp, const hco_c32* x_in, int iters, double* x_out)
+{
+  zc x[HCO_N + 1], p[HCO_NP + 1], A[HCO_N][HCO_N], b[HCO_N];
+  for (int i = 0; i < HCO_N; i++) { x[i].re = x_in[i].re; x[i].im = x_in[i].im; }
+  x[HCO_N].re = 1; x[HCO_N].im = 0;
+  for (int i = 0; i <= HCO_NP; i++) { p[i].re = tp[i].re; p[i].im = tp[i].im; }
+  double res = 0;
+  for (int it = 0; it <= iters; it++) {
+    res = 0;
+    for (int row = 0; row < HCO_N; row++) {
+      zc acc = {0, 0};
+      for (int j = 0; j < HCO_HT_TERMS; j++) {
+        const int base = (j * HCO_HT_PARTS) * HCO_N + row;
+        if (!dHdt[base]) continue;
+        zc t = {(double)dHdt[base], 0};
+        t = z_mul(t, p[dHdt[base + HCO_N]]); t = z_mul(t, p[dHdt[base + 2 * HCO_N]]);
+        t = z_mul(t, x[dHdt[base + 3 * HCO_N]]); t = z_mul(t, x[dHdt[base + 4 * HCO_N]]); t = z_mul(t, x[dHdt[base + 5 * HCO_N]]);
+        acc = z_add(acc, t);
+      }
+      b[row] = acc;
+      res += acc.re * acc.re + acc.im * acc.im;
+    }
+    if (it == iters) break;
+    for (int row = 0; row < HCO_N; row++)
+      for (int col = 0; col < HCO_N; col++) {
+        zc acc = {0, 0};
+        for (int j = 0; j < HCO_HX_TERMS; j++) {
+          const int base = (col * HCO_HX_TERMS * HCO_HX_PARTS + j * HCO_HX_PARTS) * HCO_N + row;
+          if (!dHdx[base]) continue;
+          zc t = {(double)dHdx[base], 0};
+          t = z_mul(t, p[dHdx[base + HCO_N]]); t = z_mul(t, p[dHdx[base + 2 * HCO_N]]);
+          t = z_mul(t, x[dHdx[base + 3 * HCO_N]]); t = z_mul(t, x[dHdx[base + 4 * HCO_N]]);
+          acc = z_add(acc, t);
+        }
+        A[row][col] = acc;
+      }
+    /* plain partial-pivot LU in double */
+    for (int k = 0; k < HCO_N; k++) {
+      int piv = k; double best = -1;
+      for (int i = k; i < HCO_N; i++) { double v = fabs(A[i][k].re) + fabs(A[i][k].im); if (v > best) { best = v; piv = i; } }
+      if (piv != k) { for (int j = 0; j < HCO_N; j++) { zc t = A[k][j]; A[k][j] = A[piv][j]; A[piv][j] = t; } zc t = b[k]; b[k] = b[piv]; b[piv] = t; }
+      for (int i = k + 1; i < HCO_N; i++) {
+        zc m = z_div(A[i][k], A[k][k]);
+        for (int j = k + 1; j < HCO_N; j++) A[i][j] = z_sub(A[i][j], z_mul(m, A[k][j]));
+        b[i] = z_sub(b[i], z_mul(m, b[k]));
+      }
+    }
+    for (int k = HCO_N - 1; k >= 0; k--) {
+      zc s = b[k];
+      for (int j = k + 1; j < HCO_N; j++) s = z_sub(s, z_mul(A[k][j], b[j]));
+      b[k] = z_div(s, A[k][k]);
+    }
+    for (int i = 0; i < HCO_N; i++) x[i] = z_sub(x[i], b[i]);
+  }
+  for (int i = 0; i < HCO_N; i++) { x_out[2 * i] = x[i].re; x_out[2 * i + 1] = x[i].im; }
+  return sqrt(res);
+}

@@ -1,0 +1,169 @@
+"""ctypes front-end of the CPU oracles.  TEST INFRASTRUCTURE ONLY — imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs; the product package never imports this module.
+
+  Oracle     oracle/liboracle_hc.so      plain-C restatement (hc_oracle.c), built on demand with gcc
+  Reference  oracle/_ref/libref_cpuhc.so the UNMODIFIED reference CPU-HC (built in the build container from /root/reference
+                                         by `make -C oracle ref`; travels to the GPU box as a prebuilt file)
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle_hc.so")
+REF_CPU_SO = os.path.join(HERE, "_ref", "libref_cpuhc.so")
+REF_GPU_SO = os.path.join(HERE, "_ref", "libref_gpuhc.so")
+
+N, NP1, TRACKS = 30, 34, 312
+
+
+def _vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def c2f(z):
+    """complex64 array -> float32 array with trailing (re, im)."""
+    z = np.asarray(z, np.complex64)
+    return np.ascontiguousarray(np.stack([z.real, z.imag], -1).astype(np.float32))
+
+
+def f2c(a):
+    return (a[..., 0] + 1j * a[..., 1]).astype(np.complex64)
+
+
+class Settings(ctypes.Structure):
+    _fields_ = [("max_steps", ctypes.c_int), ("max_corr_steps", ctypes.c_int), ("dt_inc_steps", ctypes.c_int),
+                ("prune", ctypes.c_int)]
+
+
+def build_oracle(force=False):
+    src = os.path.join(HERE, "hc_oracle.c")
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "oracle"], stdout=subprocess.DEVNULL)
+    return ORACLE_SO
+
+
+class Oracle:
+    def __init__(self, problem):
+        build_oracle()
+        self.lib = ctypes.CDLL(ORACLE_SO)
+        self.lib.hco_newton_refine_f64.restype = ctypes.c_double
+        self.hx = np.ascontiguousarray(problem["dHdx_indx"], np.int32)
+        self.ht = np.ascontiguousarray(problem["dHdt_indx"], np.int32)
+        ss = np.ones((TRACKS, N + 1), np.complex64)
+        ss[:, :N] = problem["start_sols"]
+        self.start_sols = ss
+        self.start_params = np.concatenate([problem["start_params"], [1.0]]).astype(np.complex64)
+        self._ss = c2f(ss)
+        self._sp = c2f(self.start_params)
+
+    # evaluators -------------------------------------------------------------------------------------------------
+    def eval_Hx(self, x31, p34):
+        A = np.zeros((N, N, 2), np.float32)
+        self.lib.hco_eval_Hx(_vp(self.hx), _vp(c2f(x31)), _vp(c2f(p34)), _vp(A))
+        return f2c(A)
+
+    def eval_H(self, x31, p34):
+        b = np.zeros((N, 2), np.float32)
+        self.lib.hco_eval_H(_vp(self.ht), _vp(c2f(x31)), _vp(c2f(p34)), _vp(b))
+        return f2c(b)
+
+    def eval_Ht(self, x31, p34, dp34):
+        b = np.zeros((N, 2), np.float32)
+        self.lib.hco_eval_Ht(_vp(self.ht), _vp(c2f(x31)), _vp(c2f(p34)), _vp(c2f(dp34)), _vp(b))
+        return f2c(b)
+
+    def param_homotopy(self, t, target34):
+        p = np.zeros((NP1, 2), np.float32)
+        self.lib.hco_param_homotopy(ctypes.c_float(t), _vp(self._sp), _vp(c2f(target34)), _vp(p))
+        return f2c(p)
+
+    def solve(self, A, b, lu_ref=False):
+        Af, bf = c2f(A), c2f(b)
+        fn = self.lib.hco_solve_lu_ref if lu_ref else self.lib.hco_solve
+        info = fn(_vp(Af), _vp(bf))
+        return f2c(bf), info
+
+    # tracker ----------------------------------------------------------------------------------------------------
+    def prepare_target_params(self, seed, n_hyp, locations, tangents):
+        tgt = np.zeros((n_hyp, NP1, 2), np.float32)
+        dif = np.zeros((n_hyp, NP1, 2), np.float32)
+        picked = np.zeros((n_hyp, 3), np.int32)
+        loc = np.ascontiguousarray(locations, np.float32)
+        tan = np.ascontiguousarray(tangents, np.float32)
+        self.lib.hco_prepare_target_params(ctypes.c_uint(seed), n_hyp, loc.shape[0], _vp(loc), _vp(tan), _vp(self._sp),
+                                           _vp(tgt), _vp(dif), _vp(picked))
+        return f2c(tgt), f2c(dif), picked
+
+    def track(self, target, diff, prune, max_steps=80, max_corr=3, dt_inc=4, n_threads=0):
+        """Returns tracks[P,31] c64, converged[P] u8, infinity[P] u8, stats[P,5] i32 (steps,pred,corr,rejected,reason)."""
+        n_hyp = target.shape[0]
+        P = n_hyp * TRACKS
+        tr = np.zeros((P, N + 1, 2), np.float32)
+        cv = np.zeros(P, np.uint8)
+        inf = np.zeros(P, np.uint8)
+        st = np.zeros((P, 5), np.int32)
+        cfg = Settings(max_steps, max_corr, dt_inc, 1 if prune else 0)
+        self.lib.hco_track_batch(_vp(self.hx), _vp(self.ht), _vp(self._ss), _vp(self._sp), _vp(c2f(target)), _vp(c2f(diff)),
+                                 n_hyp, ctypes.byref(cfg), n_threads or (os.cpu_count() or 1), _vp(tr), _vp(cv), _vp(inf), _vp(st))
+        return f2c(tr), cv, inf, st
+
+    def score(self, x31, locations, K):
+        n21, n31, gate = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        loc = np.ascontiguousarray(locations, np.float32)
+        Kf = np.ascontiguousarray(K, np.float32).reshape(-1)
+        ok = self.lib.hco_score_solution(_vp(c2f(x31)), _vp(loc), loc.shape[0], _vp(Kf), ctypes.byref(n21), ctypes.byref(n31),
+                                         ctypes.byref(gate))
+        return bool(ok), n21.value, n31.value, bool(gate.value)
+
+    def newton_refine(self, target34, x31, iters=6):
+        out = np.zeros((N, 2), np.float64)
+        res = self.lib.hco_newton_refine_f64(_vp(self.hx), _vp(self.ht), _vp(c2f(target34)), _vp(c2f(x31)), iters, _vp(out))
+        return out[:, 0] + 1j * out[:, 1], res
+
+
+class ReferenceCPU:
+    """The real reference CPU-HC (oracle/_ref/libref_cpuhc.so)."""
+
+    def __init__(self):
+        if not os.path.exists(REF_CPU_SO):
+            raise FileNotFoundError(REF_CPU_SO + " (run `make -C oracle ref` in the build container)")
+        os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+        self.lib = ctypes.CDLL(REF_CPU_SO)
+
+    def run(self, bin_dir, n_hyp, seed=0, dataset_index=0, n_cores=None, target=None):
+        P = n_hyp * TRACKS
+        tr = np.zeros((P, N + 1, 2), np.float32)
+        cv = np.zeros(P, np.uint8)
+        inf = np.zeros(P, np.uint8)
+        tp = np.zeros((n_hyp, NP1, 2), np.float32)
+        sec = ctypes.c_double()
+        tin = c2f(target) if target is not None else None
+        rc = self.lib.ref_cpuhc_run(bin_dir.encode(), n_hyp, ctypes.c_uint(seed), dataset_index, n_cores or (os.cpu_count() or 1),
+                                    _vp(tin), _vp(tr), _vp(cv), _vp(inf), _vp(tp), ctypes.byref(sec))
+        if rc != 0:
+            raise RuntimeError("ref_cpuhc_run failed with code %d" % rc)
+        return f2c(tr), cv, inf, f2c(tp), sec.value
+
+    def eval_Hx(self, hx, x31, p34):
+        A = np.zeros((N * N, 2), np.float32)
+        self.lib.ref_eval_dHdX(_vp(np.ascontiguousarray(hx, np.int32)), _vp(c2f(x31)), _vp(c2f(p34)), _vp(A))
+        return f2c(A).reshape(N, N).T      # column-major -> [row][col]
+
+    def eval_H(self, ht, x31, p34):
+        b = np.zeros((N, 2), np.float32)
+        self.lib.ref_eval_H(_vp(np.ascontiguousarray(ht, np.int32)), _vp(c2f(x31)), _vp(c2f(p34)), _vp(b))
+        return f2c(b)
+
+    def eval_Ht(self, ht, x31, p34, dp34):
+        b = np.zeros((N, 2), np.float32)
+        self.lib.ref_eval_dHdt(_vp(np.ascontiguousarray(ht, np.int32)), _vp(c2f(x31)), _vp(c2f(p34)), _vp(c2f(dp34)), _vp(b))
+        return f2c(b)
+
+    def cgesv(self, A, b):
+        Acm = c2f(np.asarray(A).T)          # row-major [row][col] -> column-major
+        bf = c2f(b)
+        info = self.lib.ref_cgesv(_vp(Acm), _vp(bf))
+        return f2c(bf), info

@@ -1,0 +1,265 @@
+#!/usr/bin/env python3
+"""Problem compiler: turns the reference's padded evaluation-index tables into a compact SIMT schedule.
+
+Input  : the two index tables of a minimal problem (reference format, SURVEY.md App. A.3;
+         `problems/trifocal_2op1p_30x30/dHdx_indx.txt`, `dHdt_indx.txt`), taken from the packaged fixture.
+Output : `csrc/hc_problem_gen.h` — tables + X-macros consumed by the CUDA tracker (`csrc/hc_tracker.cu`).
+
+What the reference does (gpu-idx-evals/dev-eval-indxing-trifocal_2op1p_30x30_LimUnroll_L2Cache.cuh:57-148):
+every lane (= matrix row) walks 30 columns x 8 padded term slots for Hx (7200 slots, 558 non-zero) and
+16 padded slots for H / Ht, reading 5-6 int32 indices per slot from a 152 KB table in global memory.
+
+What we emit instead (same arithmetic per term, see "evaluation spec" in DESIGN.md):
+  * coefficient tables: every distinct (coef, p_a, p_b) triple becomes one entry  cq = coef * p_a(t) * p_b(t)
+    (and  dq = coef * (dp_a p_b + dp_b p_a)  for Ht); the warp builds them cooperatively once per change of t;
+  * column classes: columns that never share a row (e.g. 24|27, 0|1, 2..11) are evaluated in ONE accumulator
+    per lane and scattered to the register row afterwards, so Hx needs ~32 term slots per lane instead of 240;
+  * every slot multiplies ALL factor positions, padded ones included (x[30] == 1), exactly like the reference's
+    `coef * p[a] * p[b] * x[d] * x[e]`; a lane without a term in a slot reads the zero coefficient and x[30];
+  * per-lane operands are one packed 32-bit word per slot:  cq byte offset | x_d<<10 | x_e<<15 | x_f<<20.
+Term order inside every matrix entry is the table order, so sums are bit-identical to the oracle's
+table-driven evaluation (`oracle/hc_oracle.c`).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+sys.path.insert(0, os.path.dirname(PKG))
+
+N = 30          # variables / equations
+P_PAD = 33      # parameter index that holds the constant 1
+X_PAD = 30      # variable index that holds the constant 1
+WARP = 32
+
+
+def load_tables():
+    from trifocal_pose_estimation_using_improved_gpuhc_b200 import fixtures
+    prob = fixtures.load_problem()
+    hx = prob["dHdx_indx"].reshape(N, 8, 5, N)    # [col][term][part][row]   (Data_Reader.cpp:123-165 token order)
+    ht = prob["dHdt_indx"].reshape(16, 6, N)      # [term][part][row]
+    return hx, ht
+
+
+def parse_terms(hx, ht):
+    """Return hx_terms[(row, col)] = [(coef,a,b,[x...])...], h_terms[row] = [...], in table order, zero coefs dropped."""
+    hx_terms = {}
+    for col in range(N):
+        for row in range(N):
+            lst = []
+            for t in range(hx.shape[1]):
+                c, a, b, d, e = (int(v) for v in hx[col, t, :, row])
+                if c == 0:
+                    continue
+                xs = [v for v in (d, e) if v != X_PAD]
+                assert not (a == P_PAD and b != P_PAD)
+                lst.append((c, a, b, xs))
+            if lst:
+                hx_terms[(row, col)] = lst
+    h_terms = {}
+    for row in range(N):
+        lst = []
+        for t in range(ht.shape[0]):
+            c, a, b, d, e, f = (int(v) for v in ht[t, :, row])
+            if c == 0:
+                continue
+            xs = [v for v in (d, e, f) if v != X_PAD]
+            assert not (a == P_PAD and b != P_PAD)
+            lst.append((c, a, b, xs))
+        h_terms[row] = lst
+    return hx_terms, h_terms
+
+
+def column_classes(hx_terms):
+    """Greedy colouring: two columns may share a class iff no row has a non-zero in both."""
+    rows_of = {c: {r for (r, cc) in hx_terms if cc == c} for c in range(N)}
+    order = sorted(range(N), key=lambda c: (-max((len(hx_terms[(r, c)]) for r in rows_of[c]), default=0), c))
+    classes = []
+    for c in order:
+        if not rows_of[c]:
+            continue
+        for cl in classes:
+            if all(not (rows_of[c] & rows_of[o]) for o in cl):
+                cl.append(c)
+                break
+        else:
+            classes.append([c])
+    return [sorted(cl) for cl in classes]
+
+
+def schedule(seqs):
+    """seqs[lane] = list of payloads in table order.  Slot k holds every lane's k-th term (None = no term)."""
+    n = max(len(q) for q in seqs)
+    return [[q[k] if k < len(q) else None for q in seqs] for k in range(n)]
+
+
+def build():
+    hx, ht = load_tables()
+    hx_terms, h_terms = parse_terms(hx, ht)
+
+    # ---- coefficient tables -------------------------------------------------------------------------------
+    cq_keys = set()
+    for lst in hx_terms.values():
+        cq_keys.update((c, a, b) for c, a, b, _ in lst)
+    for lst in h_terms.values():
+        cq_keys.update((c, a, b) for c, a, b, _ in lst)
+    # index 0 is the zero coefficient used by empty slots
+    cq_list = [(0, P_PAD, P_PAD)] + sorted(cq_keys, key=lambda k: (k[2] == P_PAD, k[1], k[2], k[0]))
+    cq_index = {k: i for i, k in enumerate(cq_list)}
+    dq_keys = set()
+    for lst in h_terms.values():
+        dq_keys.update((c, a, b) for c, a, b, _ in lst if not (a == P_PAD and b == P_PAD))
+    dq_list = [(0, P_PAD, P_PAD)] + sorted(dq_keys, key=lambda k: (k[2] == P_PAD, k[1], k[2], k[0]))
+    dq_index = {k: i for i, k in enumerate(dq_list)}
+
+    # ---- Hx: classes + slots ------------------------------------------------------------------------------
+    classes = column_classes(hx_terms)
+    col_class = {c: ci for ci, cl in enumerate(classes) for c in cl}
+    hx_slots = []      # (class, [payload]*32)
+    for ci, cl in enumerate(classes):
+        seqs = []
+        for lane in range(WARP):
+            seq = []
+            if lane < N:
+                cols = [c for c in cl if (lane, c) in hx_terms]
+                assert len(cols) <= 1
+                if cols:
+                    for c, a, b, xs in hx_terms[(lane, cols[0])]:
+                        seq.append((cq_index[(c, a, b)], xs))
+            seqs.append(seq)
+        for row in schedule(seqs):
+            hx_slots.append((ci, row))
+
+    def sched_rows(terms_of_row, index, drop_const):
+        seqs = []
+        for lane in range(WARP):
+            seq = []
+            if lane < N:
+                for c, a, b, xs in terms_of_row[lane]:
+                    if drop_const and a == P_PAD and b == P_PAD:
+                        continue      # d/dt of a parameter-free term vanishes (…L2Cache.cuh:107-118 adds an exact 0)
+                    seq.append((index[(c, a, b)], xs))
+            seqs.append(seq)
+        return schedule(seqs)
+
+    h_slots = sched_rows(h_terms, cq_index, False)
+    ht_slots = sched_rows(h_terms, dq_index, True)
+    return dict(hx_terms=hx_terms, h_terms=h_terms, cq_list=cq_list, dq_list=dq_list, classes=classes,
+                col_class=col_class, hx_slots=hx_slots, h_slots=h_slots, ht_slots=ht_slots)
+
+
+def pack_word(payload):
+    if payload is None:
+        idx, xs = 0, []
+    else:
+        idx, xs = payload
+    xs = list(xs) + [X_PAD] * (3 - len(xs))
+    assert idx * 8 < 1024
+    return (idx * 8) | (xs[0] << 10) | (xs[1] << 15) | (xs[2] << 20)
+
+
+def pack_build_word(key):
+    c, a, b = key
+    # a_off (9 bits) | b_off (9 bits) << 9 | (coef + 2) << 18
+    return (a * 8) | ((b * 8) << 9) | ((c + 2) << 18)
+
+
+def emit(g, path):
+    ncq, ndq = len(g["cq_list"]), len(g["dq_list"])
+    rounds = lambda n: (n + WARP - 1) // WARP
+    L = []
+    w = L.append
+    w("// GENERATED by codegen/gen_eval.py from the problem's evaluation-index tables — do not edit.")
+    w("// Problem: trifocal_2op1p_30x30 (30 equations, 30 unknowns, 33 parameters, 312 paths).")
+    w("#ifndef HC_PROBLEM_GEN_H")
+    w("#define HC_PROBLEM_GEN_H")
+    w("#define HCG_N %d" % N)
+    w("#define HCG_NUM_PARAMS 33")
+    w("#define HCG_NUM_CQ %d   /* coef*p_a*p_b table (entry 0 == 0) */" % ncq)
+    w("#define HCG_NUM_DQ %d   /* coef*(dp_a*p_b + dp_b*p_a) table (entry 0 == 0) */" % ndq)
+    w("#define HCG_CQ_ROUNDS %d" % rounds(ncq))
+    w("#define HCG_DQ_ROUNDS %d" % rounds(ndq))
+    w("#define HCG_NUM_CLASSES %d" % len(g["classes"]))
+    w("#define HCG_HX_SLOTS %d" % len(g["hx_slots"]))
+    w("#define HCG_H_SLOTS %d" % len(g["h_slots"]))
+    w("#define HCG_HT_SLOTS %d" % len(g["ht_slots"]))
+    nnz = len(g["hx_terms"])
+    nterms = sum(len(v) for v in g["hx_terms"].values())
+    w("#define HCG_HX_NNZ %d" % nnz)
+    w("#define HCG_HX_TERMS %d" % nterms)
+    w("#define HCG_H_TERMS %d" % sum(len(v) for v in g["h_terms"].values()))
+    # word table layout: [cq build rounds][dq build rounds][hx slots][h slots][ht slots], 32 words each
+    off_cq = 0
+    off_dq = off_cq + rounds(ncq)
+    off_hx = off_dq + rounds(ndq)
+    off_h = off_hx + len(g["hx_slots"])
+    off_ht = off_h + len(g["h_slots"])
+    total = off_ht + len(g["ht_slots"])
+    w("#define HCG_TBL_CQ %d" % off_cq)
+    w("#define HCG_TBL_DQ %d" % off_dq)
+    w("#define HCG_TBL_HX %d" % off_hx)
+    w("#define HCG_TBL_H %d" % off_h)
+    w("#define HCG_TBL_HT %d" % off_ht)
+    w("#define HCG_TBL_ROWS %d" % total)
+    rows = []
+    for lst, n in ((g["cq_list"], ncq), (g["dq_list"], ndq)):
+        for r in range(rounds(n)):
+            rows.append([pack_build_word(lst[r * WARP + l]) if r * WARP + l < n else pack_build_word((0, P_PAD, P_PAD))
+                         for l in range(WARP)])
+    for _, row in g["hx_slots"]:
+        rows.append([pack_word(p) for p in row])
+    for row in g["h_slots"]:
+        rows.append([pack_word(p) for p in row])
+    for row in g["ht_slots"]:
+        rows.append([pack_word(p) for p in row])
+    assert len(rows) == total
+    w("// packed per-lane operand words, [row][lane]")
+    w("#define HCG_TBL_INIT { \\")
+    for r in rows:
+        w("  " + ",".join("0x%08xu" % v for v in r) + ", \\")
+    w("}")
+    # per-lane bitmask of structurally non-zero columns (row = lane)
+    masks = []
+    for lane in range(WARP):
+        m = 0
+        for c in range(N):
+            if (lane, c) in g["hx_terms"]:
+                m |= 1 << c
+        masks.append(m)
+    w("#define HCG_NZMASK_INIT { " + ",".join("0x%08xu" % m for m in masks) + " }")
+    w("// X(slot, class): one Hx term slot; acc[class] += cq * x_d * x_e")
+    w("#define HCG_HX_SLOT_LIST(X) \\")
+    for s, (ci, _) in enumerate(g["hx_slots"]):
+        w("  X(%d, %d) \\" % (s, ci))
+    w("")
+    w("// X(col, class): rA[col] = lane has a non-zero in col ? acc[class] : 0")
+    w("#define HCG_HX_SCATTER_LIST(X) \\")
+    for c in range(N):
+        w("  X(%d, %d) \\" % (c, g["col_class"].get(c, 0)))
+    w("")
+
+    w("#endif")
+    text = "\n".join(L) + "\n"
+    with open(path, "w") as f:
+        f.write(text)
+    return text
+
+
+def main():
+    g = build()
+    out = os.path.join(PKG, "csrc", "hc_problem_gen.h")
+    emit(g, out)
+    print("classes:", g["classes"])
+    print("cq entries %d, dq entries %d" % (len(g["cq_list"]), len(g["dq_list"])))
+    print("Hx slots %d (ref 240), H slots %d (ref 16), Ht slots %d (ref 16)" %
+          (len(g["hx_slots"]), len(g["h_slots"]), len(g["ht_slots"])))
+    print("hx_slots", [(ci, sum(p is not None for p in row)) for ci, row in g["hx_slots"]])
+    print("h_slots", [sum(p is not None for p in row) for row in g["h_slots"]])
+    print("ht_slots", [sum(p is not None for p in row) for row in g["ht_slots"]])
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,256 @@
+"""ctypes binding of the C ABI (`include/hcb200.h`) plus the thin host logic the benchmarks and tests need.
+
+PyTorch is used for device memory, streams and `torch.distributed` only; every kernel launched here lives in
+`lib/libhcb200.so` (built by `make` / `__graft_entry__.build()`).  There is NO CPU fallback: if the library is missing
+or a launch fails this module raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import fixtures
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhcb200.so")
+
+NUM_VARS = 30
+NUM_PARAMS = 33
+NUM_TRACKS = 312
+FLAG_PRUNE_PATHS = 1
+
+_lib = None
+
+# every symbol include/hcb200.h declares
+ABI_SYMBOLS = ("hcb200_workspace_bytes", "hcb200_abi_version", "hcb200_track", "hcb200_track_abort",
+               "hcb200_build_target_params", "hcb200_kernel_info", "hcb200_error_string")
+
+
+class HCB200Error(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """Load libhcb200.so (once).  Raises HCB200Error when it has not been built — never falls back to the CPU."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise HCB200Error("CUDA extension %s is missing: run `make` (or __graft_entry__.build()) first" % path)
+    lib = ctypes.CDLL(path)
+    vp, i32, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint
+    lib.hcb200_workspace_bytes.restype = ctypes.c_size_t
+    lib.hcb200_workspace_bytes.argtypes = []
+    lib.hcb200_abi_version.restype = i32
+    lib.hcb200_error_string.restype = ctypes.c_char_p
+    lib.hcb200_error_string.argtypes = [i32]
+    lib.hcb200_track.restype = i32
+    lib.hcb200_track.argtypes = [vp, i32, i32, i32, i32, u32] + [vp] * 9
+    lib.hcb200_track_abort.restype = i32
+    lib.hcb200_track_abort.argtypes = [vp, i32, i32, i32, i32, i32, u32] + [vp] * 14
+    lib.hcb200_build_target_params.restype = i32
+    lib.hcb200_build_target_params.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp]
+    lib.hcb200_kernel_info.restype = i32
+    lib.hcb200_kernel_info.argtypes = [i32] + [ctypes.POINTER(i32)] * 5
+    _lib = lib
+    return lib
+
+
+def _check(code, what):
+    if code != 0:
+        msg = load_library().hcb200_error_string(code)
+        raise HCB200Error("%s failed: cudaError %d (%s)" % (what, code, msg.decode() if msg else "?"))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# host logic mirrored from the reference (no device work)
+
+def shard_sizes(n_hyp, n_gpus):
+    """GPU_HC_Solver.cpp:85-88: sub_RANSAC_iters[g] = H / N + (g < H % N)."""
+    return [n_hyp // n_gpus + (1 if g < n_hyp % n_gpus else 0) for g in range(n_gpus)]
+
+
+def shard_offsets(n_hyp, n_gpus):
+    sizes = shard_sizes(n_hyp, n_gpus)
+    offs = [0]
+    for s in sizes:
+        offs.append(offs[-1] + s)
+    return offs
+
+
+_libc = None
+
+
+def sample_hypotheses(seed, n_hyp, n_edgels):
+    """GPU_HC_Solver.cpp:263-271: srand(seed); three rand() % E per attempt, accept when e0 != e1 and e1 != e2
+    (the reference never checks e0 != e2).  Uses the C library's rand() stream."""
+    global _libc
+    if _libc is None:
+        _libc = ctypes.CDLL(None)
+        _libc.rand.restype = ctypes.c_int
+        _libc.srand.argtypes = [ctypes.c_uint]
+    _libc.srand(seed)
+    out = np.empty((n_hyp, 3), np.int32)
+    for h in range(n_hyp):
+        while True:
+            e = [_libc.rand() % n_edgels for _ in range(3)]
+            if e[0] != e[1] and e[1] != e[2]:
+                break
+        out[h] = e
+    return out
+
+
+def target_params_from_picks(picked, locations, tangents, start_params):
+    """GPU_HC_Solver.cpp:276-296 on the host, vectorised.  Returns (target[H,34], diff[H,34]) complex64."""
+    picked = np.asarray(picked)
+    H = picked.shape[0]
+    tgt = np.zeros((H, NUM_PARAMS + 1), np.complex64)
+    tgt[:, 0:18] = locations[picked].reshape(H, 18)
+    tgt[:, 18:30] = tangents[picked[:, :2]].reshape(H, 12)
+    tgt[:, 30] = 1.0
+    tgt[:, 31] = 0.5
+    tgt[:, 32] = 1.0
+    tgt[:, 33] = 1.0
+    sp = np.concatenate([np.asarray(start_params, np.complex64)[:NUM_PARAMS], [1.0]]).astype(np.complex64)
+    diff = np.empty_like(tgt)
+    diff.real = tgt.real - sp.real[None, :]
+    diff.imag = tgt.imag - sp.imag[None, :]
+    return tgt, diff
+
+
+def padded_start_sols(start_sols):
+    """[312,30] -> [312,31] with the constant-one pad (Data_Reader.cpp:55-57)."""
+    ss = np.ones((NUM_TRACKS, NUM_VARS + 1), np.complex64)
+    ss[:, :NUM_VARS] = start_sols
+    return ss
+
+
+def padded_start_params(start_params):
+    return np.concatenate([np.asarray(start_params, np.complex64)[:NUM_PARAMS], [1.0]]).astype(np.complex64)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+
+class Tracker:
+    """Device-side state of one GPU's share of a RANSAC round (mirrors the per-GPU arrays of GPU_HC_Solver,
+    GPU_HC_Solver.cpp:137-184) and the two launches.  All tensors are torch CUDA tensors owned by this object."""
+
+    def __init__(self, device=None, problem=None, max_steps=80, max_corr=3, dt_inc=4, stats=False):
+        import torch
+        self.torch = torch
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise HCB200Error("no CUDA device: the tracker has no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        problem = problem or fixtures.load_problem()
+        self.max_steps, self.max_corr, self.dt_inc = max_steps, max_corr, dt_inc
+        self.start_sols_h = padded_start_sols(problem["start_sols"])
+        self.start_params_h = padded_start_params(problem["start_params"])
+        with torch.cuda.device(self.device):
+            self.d_start_sols = torch.view_as_real(torch.from_numpy(self.start_sols_h)).contiguous().to(self.device)
+            self.d_start_params = torch.view_as_real(torch.from_numpy(self.start_params_h)).contiguous().to(self.device)
+            self.d_ws = torch.zeros(int(self.lib.hcb200_workspace_bytes()), dtype=torch.uint8, device=self.device)
+        self.capacity = 0
+        self.launches = 0
+        self.want_stats = stats
+        self.d_stats = None
+
+    def kernel_info(self, abort=False):
+        v = [ctypes.c_int() for _ in range(5)]
+        with self.torch.cuda.device(self.device):
+            _check(self.lib.hcb200_kernel_info(1 if abort else 0, *[ctypes.byref(x) for x in v]), "hcb200_kernel_info")
+        return dict(zip(("regs", "smem_bytes", "ctas_per_sm", "grid", "block"), [x.value for x in v]))
+
+    def reserve(self, n_hyp):
+        torch = self.torch
+        stats = self.want_stats
+        if n_hyp <= self.capacity:
+            return
+        n_paths = n_hyp * NUM_TRACKS
+        dev = self.device
+        self.d_target = torch.empty((n_hyp, NUM_PARAMS + 1, 2), dtype=torch.float32, device=dev)
+        self.d_diff = torch.empty_like(self.d_target)
+        self.d_tracks = torch.empty((n_paths, NUM_VARS + 1, 2), dtype=torch.float32, device=dev)
+        self.d_conv = torch.empty(n_paths, dtype=torch.uint8, device=dev)
+        self.d_inf = torch.empty(n_paths, dtype=torch.uint8, device=dev)
+        self.d_stats = torch.empty((n_paths, 4), dtype=torch.int32, device=dev) if stats else None
+        self.d_found = torch.zeros(1, dtype=torch.uint8, device=dev)
+        self.d_found_index = torch.empty(n_paths, dtype=torch.int32, device=dev)
+        self.d_best = torch.zeros(16, dtype=torch.int32, device=dev)
+        self.capacity = n_hyp
+
+    def set_edgels(self, locations, K):
+        torch = self.torch
+        self.d_edgels = torch.from_numpy(np.ascontiguousarray(locations, np.float32)).to(self.device)
+        self.d_K = torch.from_numpy(np.ascontiguousarray(K, np.float32).reshape(-1)).to(self.device)
+        self.n_edgels = int(locations.shape[0])
+
+    def upload_params(self, target, diff, non_blocking=False):
+        """target/diff: complex64 numpy [H,34] or pinned float32 torch tensors [H,34,2]."""
+        torch = self.torch
+        if isinstance(target, np.ndarray):
+            target = torch.view_as_real(torch.from_numpy(np.ascontiguousarray(target, np.complex64)))
+            diff = torch.view_as_real(torch.from_numpy(np.ascontiguousarray(diff, np.complex64)))
+        H = target.shape[0]
+        self.reserve(H)
+        self.d_target[:H].copy_(target, non_blocking=non_blocking)
+        self.d_diff[:H].copy_(diff, non_blocking=non_blocking)
+        return H
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def track(self, n_hyp, prune=True):
+        """Enqueue hcb200_track on torch's current stream (asynchronous, like the reference wrapper)."""
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        with self.torch.cuda.device(self.device):
+            rc = self.lib.hcb200_track(self._stream(), n_hyp, self.max_steps, self.max_corr, self.dt_inc,
+                                       FLAG_PRUNE_PATHS if prune else 0,
+                                       p(self.d_start_sols), p(self.d_start_params), p(self.d_target), p(self.d_diff),
+                                       p(self.d_tracks), p(self.d_conv), p(self.d_inf), p(self.d_stats), p(self.d_ws))
+        _check(rc, "hcb200_track")
+        self.launches += 1
+
+    def track_abort(self, n_hyp, prune=True):
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        n_paths = n_hyp * NUM_TRACKS
+        self.d_found.zero_()
+        self.d_found_index[:n_paths].fill_(-1)
+        with self.torch.cuda.device(self.device):
+            rc = self.lib.hcb200_track_abort(self._stream(), n_hyp, self.n_edgels, self.max_steps, self.max_corr, self.dt_inc,
+                                             FLAG_PRUNE_PATHS if prune else 0,
+                                             p(self.d_start_sols), p(self.d_start_params), p(self.d_target), p(self.d_diff),
+                                             p(self.d_edgels), p(self.d_K),
+                                             p(self.d_tracks), p(self.d_conv), p(self.d_inf),
+                                             p(self.d_found), p(self.d_found_index), p(self.d_best),
+                                             p(self.d_stats), p(self.d_ws))
+        _check(rc, "hcb200_track_abort")
+        self.launches += 2
+
+    def build_target_params(self, d_picked, d_tangents, n_hyp):
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with self.torch.cuda.device(self.device):
+            rc = self.lib.hcb200_build_target_params(self._stream(), n_hyp, p(d_picked), self.n_edgels, p(self.d_edgels),
+                                                     p(d_tangents), p(self.d_start_params), p(self.d_target), p(self.d_diff))
+        _check(rc, "hcb200_build_target_params")
+        self.launches += 1
+
+    def results(self, n_hyp):
+        """Synchronise and fetch (tracks complex64 [P,31], converged uint8 [P], infinity uint8 [P], stats or None)."""
+        self.torch.cuda.synchronize(self.device)
+        n = n_hyp * NUM_TRACKS
+        tr = self.d_tracks[:n].cpu().numpy()
+        tracks = (tr[..., 0] + 1j * tr[..., 1]).astype(np.complex64)
+        stats = self.d_stats[:n].cpu().numpy() if self.d_stats is not None else None
+        return tracks, self.d_conv[:n].cpu().numpy(), self.d_inf[:n].cpu().numpy(), stats
+
+
+def count_solutions(tracks, converged, infinity, n_hyp):
+    """Evaluations::Evaluate_HC_Sols (Evaluations.cpp:145-167): per hypothesis (#converged, #infinity, #real) with
+    real == converged and all 30 |imag| <= 1e-4 (ZERO_IMAG_PART_TOL_FOR_SP)."""
+    conv = converged.reshape(n_hyp, NUM_TRACKS).astype(bool)
+    inf = infinity.reshape(n_hyp, NUM_TRACKS).astype(bool)
+    im = np.abs(tracks.reshape(n_hyp, NUM_TRACKS, NUM_VARS + 1)[:, :, :NUM_VARS].imag)
+    real = conv & np.all(im.astype(np.float64) <= 1e-4, axis=2)
+    return np.stack([conv.sum(1), inf.sum(1), real.sum(1)], axis=1)
