@@ -94,6 +94,11 @@ int hcb200_build_target_params(void* stream, int n_hyp, const int32_t* d_picked,
  * grid size a launch would use on the current device.  Any pointer may be NULL. */
 int hcb200_kernel_info(int abort_variant, int* regs, int* smem_bytes, int* ctas_per_sm, int* grid, int* block);
 
+/* Benchmark helper: enqueue an FP32 FFMA issue-rate probe (16 independent chains per thread, 8 CTAs of 256 threads per
+ * SM); *flops_out = floating-point operations performed.  bench.py times it to obtain the measured FP32 peak that the
+ * tracker's roofline fraction is quoted against (MEASURED_PEAKS.json has no FP32 entry). */
+int hcb200_ffma_probe(void* stream, int iters, float* d_scratch, double* flops_out);
+
 const char* hcb200_error_string(int code);
 
 #ifdef __cplusplus

@@ -30,18 +30,19 @@ static inline hco_c32 c_msub(hco_c32 acc, hco_c32 m, hco_c32 u)
   float im = fmaf(-m.re, u.im, acc.im); im = fmaf(-m.im, u.re, im);
   return c_make(re, im);
 }
-/* 1/z with the scaling of cuCdivf (MAGMA_C_DIV, dev-cgesv-batched-small.cuh:84) */
+/* 1/z = conj(z) / |z|^2 with ONE IEEE reciprocal.  The reference divides with cuCdivf (MAGMA_C_DIV,
+ * dev-cgesv-batched-small.cuh:84), which pre-scales by |re|+|im| to survive |z| outside [1e-19, 1e19]; pivots of this
+ * system never leave that range unless the matrix is numerically singular, and the unscaled form saves a reciprocal
+ * per elimination step on the device. */
 static inline hco_c32 c_recip(hco_c32 z)
 {
-  float s = fabsf(z.re) + fabsf(z.im);
-  float oos = 1.0f / s;
-  float a = z.re * oos, b = z.im * oos;
-  float d = fmaf(a, a, b * b);
+  float d = fmaf(z.re, z.re, z.im * z.im);
   float q = 1.0f / d;
-  float t = oos * q;
-  return c_make(a * t, -(b * t));
+  return c_make(z.re * q, -(z.im * q));
 }
 static inline uint32_t f_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+/* pivot key as the device sees it: NaN is the canonical 0x7fffffff */
+static inline uint32_t key_bits(float f) { return (f != f) ? 0x7fffffffu : f_bits(f); }
 
 /* ------------------------------------------------------------------------------------------------------------
  * evaluators — literal restatement of cpu-eval-indx_trifocal_2op1p_30x30.hpp:22-89: every factor position is
@@ -133,7 +134,7 @@ int hco_solve(hco_c32* A, hco_c32* b)
     uint32_t maxbits = 0;
     uint32_t key[HCO_N];
     for (int i = 0; i < HCO_N; i++) {
-      key[i] = done[i] ? 0u : f_bits(fabsf(A[i * HCO_N + k].re) + fabsf(A[i * HCO_N + k].im));
+      key[i] = done[i] ? 0u : key_bits(fabsf(A[i * HCO_N + k].re) + fabsf(A[i * HCO_N + k].im));
       if (key[i] > maxbits) maxbits = key[i];
     }
     int p = -1, ppos = 1 << 30, q = -1;

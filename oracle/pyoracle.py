@@ -167,3 +167,77 @@ class ReferenceCPU:
         bf = c2f(b)
         info = self.lib.ref_cgesv(_vp(Acm), _vp(bf))
         return f2c(bf), info
+
+
+class ReferenceGPU:
+    """The UNMODIFIED reference GPU-HC++ kernels compiled for sm_100a (oracle/_ref/libref_gpuhc.so), driven the way
+    GPU_HC_Solver drives them.  GPU box only; used as the GPU baseline in bench.py and as a second oracle in tests."""
+
+    def __init__(self, problem, device="cuda:0"):
+        import torch
+        if not os.path.exists(REF_GPU_SO):
+            raise FileNotFoundError(REF_GPU_SO + " (run `make -C oracle ref` in the build container)")
+        self.torch = torch
+        self.lib = ctypes.CDLL(REF_GPU_SO)
+        self.device = torch.device(device)
+        ss = np.ones((TRACKS, N + 1), np.complex64)
+        ss[:, :N] = problem["start_sols"]
+        sp = np.concatenate([problem["start_params"], [1.0]]).astype(np.complex64)
+        idx = np.concatenate([problem["dHdx_indx"], problem["dHdt_indx"]]).astype(np.int32)
+        self.d_ss = torch.from_numpy(c2f(ss)).to(self.device)
+        self.d_sp = torch.from_numpy(c2f(sp)).to(self.device)
+        self.d_idx = torch.from_numpy(idx).to(self.device)
+        self.n_hyp = 0
+
+    def _s(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def setup(self, target, diff, locations=None, K=None):
+        torch = self.torch
+        H = target.shape[0]
+        P = H * TRACKS
+        dev = self.device
+        self.n_hyp = H
+        self.d_target = torch.from_numpy(c2f(target)).to(dev)
+        self.d_diff = torch.from_numpy(c2f(diff)).to(dev)
+        self.d_tracks = torch.empty((P, N + 1, 2), dtype=torch.float32, device=dev)
+        self.d_conv = torch.zeros(P, dtype=torch.bool, device=dev)
+        self.d_inf = torch.zeros(P, dtype=torch.bool, device=dev)
+        self.d_dbg = torch.zeros((P, 2), dtype=torch.float32, device=dev)
+        if locations is not None:
+            self.d_edgels = torch.from_numpy(np.ascontiguousarray(locations, np.float32)).to(dev)
+            self.d_K = torch.from_numpy(np.ascontiguousarray(K, np.float32).reshape(-1)).to(dev)
+            self.n_edgels = int(locations.shape[0])
+            self.d_found = torch.zeros(1, dtype=torch.bool, device=dev)
+            self.d_found_index = torch.full((P,), -1, dtype=torch.int32, device=dev)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        rc = self.lib.ref_gpuhc_prepare(self._s(), H, p(self.d_ss), p(self.d_tracks), p(self.d_idx), int(self.d_idx.numel()))
+        if rc:
+            raise RuntimeError("ref_gpuhc_prepare -> %d" % rc)
+
+    def reload(self):
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        self.lib.ref_gpuhc_reload_tracks(self._s(), self.n_hyp, p(self.d_ss), p(self.d_tracks))
+        self.d_inf.zero_()
+
+    def track(self, max_steps=80, max_corr=3, dt_inc=4):
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        rc = self.lib.ref_gpuhc_track(self._s(), self.n_hyp, max_steps, max_corr, dt_inc, p(self.d_sp), p(self.d_target),
+                                      p(self.d_diff), p(self.d_idx), p(self.d_conv), p(self.d_inf), p(self.d_dbg))
+        if rc:
+            raise RuntimeError("ref_gpuhc_track -> cudaError %d" % rc)
+
+    def track_abort(self, max_steps=80, max_corr=3, dt_inc=4):
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        self.d_found.zero_()
+        self.d_found_index.fill_(-1)
+        rc = self.lib.ref_gpuhc_track_abort(self._s(), self.n_hyp, self.n_edgels, max_steps, max_corr, dt_inc, p(self.d_sp),
+                                            p(self.d_target), p(self.d_diff), p(self.d_idx), p(self.d_edgels), p(self.d_K),
+                                            p(self.d_conv), p(self.d_inf), p(self.d_dbg), p(self.d_found), p(self.d_found_index))
+        if rc:
+            raise RuntimeError("ref_gpuhc_track_abort -> cudaError %d" % rc)
+
+    def results(self):
+        self.torch.cuda.synchronize(self.device)
+        tr = self.d_tracks.cpu().numpy()
+        return f2c(tr), self.d_conv.cpu().numpy().astype(np.uint8), self.d_inf.cpu().numpy().astype(np.uint8)

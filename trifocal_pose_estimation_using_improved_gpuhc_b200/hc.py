@@ -23,7 +23,7 @@ _lib = None
 
 # every symbol include/hcb200.h declares
 ABI_SYMBOLS = ("hcb200_workspace_bytes", "hcb200_abi_version", "hcb200_track", "hcb200_track_abort",
-               "hcb200_build_target_params", "hcb200_kernel_info", "hcb200_error_string")
+               "hcb200_build_target_params", "hcb200_kernel_info", "hcb200_ffma_probe", "hcb200_error_string")
 
 
 class HCB200Error(RuntimeError):
@@ -53,6 +53,8 @@ def load_library(path=None):
     lib.hcb200_build_target_params.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp]
     lib.hcb200_kernel_info.restype = i32
     lib.hcb200_kernel_info.argtypes = [i32] + [ctypes.POINTER(i32)] * 5
+    lib.hcb200_ffma_probe.restype = i32
+    lib.hcb200_ffma_probe.argtypes = [vp, i32, vp, ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib
 
@@ -235,6 +237,22 @@ class Tracker:
                                                      p(d_tangents), p(self.d_start_params), p(self.d_target), p(self.d_diff))
         _check(rc, "hcb200_build_target_params")
         self.launches += 1
+
+    def ffma_probe(self, iters=20000, reps=5):
+        """Measured FP32 FMA throughput of this GPU in TFLOP/s (best of `reps`, CUDA events)."""
+        torch = self.torch
+        scratch = torch.zeros(4, dtype=torch.float32, device=self.device)
+        flops = ctypes.c_double()
+        best = 0.0
+        for _ in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _check(self.lib.hcb200_ffma_probe(self._stream(), iters, ctypes.c_void_p(scratch.data_ptr()), ctypes.byref(flops)),
+                   "hcb200_ffma_probe")
+            e1.record()
+            e1.synchronize()
+            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        return best
 
     def results(self, n_hyp):
         """Synchronise and fetch (tracks complex64 [P,31], converged uint8 [P], infinity uint8 [P], stats or None)."""
