@@ -15,7 +15,7 @@ HOST   := $(PKG)/host
 
 .PHONY: all product oracle ref clean
 all: product
-product: $(LIBDIR)/libhcb200.so
+product: $(LIBDIR)/libhcb200.so $(LIBDIR)/libhcb200_host.so $(LIBDIR)/hc-main
 
 $(LIBDIR)/libhcb200.so: $(CSRC)/hc_tracker.cu $(CSRC)/hc_problem_gen.h include/hcb200.h
 	mkdir -p $(LIBDIR)

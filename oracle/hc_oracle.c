@@ -1,6 +1,6 @@
 /* hc_oracle.c — see hc_oracle.h.  TEST INFRASTRUCTURE ONLY (never linked into the product).
  *
- * Build: gcc -std=c11 -O2 -ffp-contract=off -fno-fast-math -fopenmp -fPIC -shared hc_oracle.c -lm
+ * Build: gcc -std=c11 -O2 -march=x86-64-v3 -ffp-contract=off -fno-fast-math -fopenmp -fPIC -shared hc_oracle.c -lm
  * -ffp-contract=off matters: every fused multiply-add below is an explicit fmaf(), every other operation is
  * individually rounded (IEEE-754 binary32, round to nearest even, denormals kept) — the same contract the CUDA
  * kernels are compiled under (-fmad=false + explicit fmaf, -prec-div=true, -prec-sqrt=true, -ftz=false).

@@ -1,0 +1,138 @@
+"""CPU-only tests of the boundary and the host logic: the C-ABI libraries load and export every declared symbol, the product
+fails loudly without a GPU, the reference text formats round-trip through Data_Reader, and the sharding / sampling logic
+matches the reference formulas.  No compute call is made on a device here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from trifocal_pose_estimation_using_improved_gpuhc_b200 import fixtures, hc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBDIR = os.path.join(ROOT, "trifocal_pose_estimation_using_improved_gpuhc_b200", "lib")
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hcb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_device_library_exports_every_declared_symbol():
+    lib = hc.load_library()
+    names = _declared("hcb200.h")
+    assert len(names) >= 8
+    for n in names:
+        assert hasattr(lib, n), "libhcb200.so does not export " + n
+    assert set(names) == set(hc.ABI_SYMBOLS)
+    assert lib.hcb200_abi_version() == 1
+    assert lib.hcb200_workspace_bytes() >= 16
+
+
+def test_host_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(os.path.join(LIBDIR, "libhcb200_host.so"))
+    for n in _declared("hcb200_host.h"):
+        assert hasattr(lib, n), "libhcb200_host.so does not export " + n
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(hc.HCB200Error):
+        hc.Tracker()
+    with pytest.raises(hc.HCB200Error):
+        hc.load_library(os.path.join(LIBDIR, "does_not_exist.so"))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "trifocal_pose_estimation_using_improved_gpuhc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".hpp", ".h", ".cuh")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "pyoracle" not in text and "hc_oracle" not in text.replace("oracle/hc_oracle.c", ""), f
+
+
+def test_shard_sizes_reference_formula():
+    # GPU_HC_Solver.cpp:85-88
+    for H in (1, 7, 100, 1000, 100003):
+        for n in range(1, 9):
+            s = hc.shard_sizes(H, n)
+            assert sum(s) == H and max(s) - min(s) <= 1 and s == sorted(s, reverse=True)
+            assert s == [H // n + (1 if g < H % n else 0) for g in range(n)]
+    assert hc.shard_sizes(100, 8) == [13, 13, 13, 13, 12, 12, 12, 12]
+    assert hc.shard_offsets(100, 3) == [0, 34, 67, 100]
+
+
+def test_python_sampler_matches_oracle_and_is_shard_invariant(oracle, ransac0, problem):
+    tgt, dif, picked = oracle.prepare_target_params(0, 40, ransac0["locations"], ransac0["tangents"])
+    mine = hc.sample_hypotheses(0, 40, 5117)
+    assert np.array_equal(mine, picked)
+    t2, d2 = hc.target_params_from_picks(mine, ransac0["locations"], ransac0["tangents"], problem["start_params"])
+    assert np.array_equal(t2, tgt) and np.array_equal(d2, dif)
+    # one rand() stream consumed in GPU-major order: the union of the shards is the single-GPU sequence
+    for n in (2, 3, 8):
+        offs = hc.shard_offsets(40, n)
+        assert np.array_equal(np.concatenate([mine[offs[g]:offs[g + 1]] for g in range(n)]), picked)
+
+
+@pytest.fixture(scope="module")
+def tree(tmp_path_factory):
+    root = str(tmp_path_factory.mktemp("tree"))
+    fixtures.materialize_tree(root, files=[0])
+    return root
+
+
+def test_data_reader_reads_reference_formats_bit_exactly(tree, problem, ransac0):
+    lib = ctypes.CDLL(os.path.join(LIBDIR, "libhcb200_host.so"))
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    ss = np.zeros((312, 31, 2), np.float32)
+    sp = np.zeros((34, 2), np.float32)
+    hx = np.zeros(36000, np.int32)
+    ht = np.zeros(2880, np.int32)
+    n = ctypes.c_int()
+    loc = np.zeros((6000, 6), np.float32)
+    tan = np.zeros((6000, 6), np.float32)
+    p21, p31, K = np.zeros(12, np.float32), np.zeros(12, np.float32), np.zeros(9, np.float32)
+    pdir = os.path.join(tree, "problems", "trifocal_2op1p_30x30").encode()
+    rdir = os.path.join(tree, "RANSAC_Data", "trifocal_2op1p_30x30", "Synthetic").encode()
+    rc = lib.hcb200_reader_load(pdir, rdir, 0, vp(ss), vp(sp), vp(hx), vp(ht), ctypes.byref(n), vp(loc), vp(tan), 6000, vp(p21), vp(p31), vp(K))
+    assert rc == 0 and n.value == 5117
+    assert np.array_equal(ss[:, :30, 0] + 1j * ss[:, :30, 1], problem["start_sols"])
+    assert np.all(ss[:, 30, 0] == 1) and np.all(ss[:, 30, 1] == 0)            # constant-one pad (Data_Reader.cpp:55-57)
+    assert np.array_equal(sp[:33, 0] + 1j * sp[:33, 1], problem["start_params"]) and sp[33].tolist() == [1, 0]
+    assert np.array_equal(hx, problem["dHdx_indx"]) and np.array_equal(ht, problem["dHdt_indx"])
+    assert np.array_equal(loc[:5117], ransac0["locations"]) and np.array_equal(tan[:5117], ransac0["tangents"])
+    assert np.array_equal(p21.reshape(4, 3), ransac0["gt_pose21"]) and np.array_equal(p31.reshape(4, 3), ransac0["gt_pose31"])
+    assert np.array_equal(K.reshape(3, 3), ransac0["K"])
+    # a missing dataset file is reported, not papered over
+    rc = lib.hcb200_reader_load(pdir, rdir, 57, vp(ss), vp(sp), vp(hx), vp(ht), ctypes.byref(n), vp(loc), vp(tan), 6000, vp(p21), vp(p31), vp(K))
+    assert rc == 5 and n.value == 0
+
+
+def test_settings_reader_understands_the_reference_yaml(tree):
+    lib = ctypes.CDLL(os.path.join(LIBDIR, "libhcb200_host.so"))
+    path = os.path.join(tree, "problems", "trifocal_2op1p_30x30", "gpuhc_settings.yaml").encode()
+    buf = ctypes.create_string_buffer(256)
+    expect = {"problem_name": "trifocal_2op1p_30x30", "Num_Of_GPUs": "1", "GPUHC_Max_Steps": "80", "GPUHC_Max_Correction_Steps": "3",
+              "GPUHC_Num_Of_Steps_to_Increase_Delta_t": "4", "Num_Of_Vars": "30", "Num_Of_Params": "33", "Num_Of_Tracks": "312",
+              "dHdx_Max_Terms": "8", "dHdx_Max_Parts": "5", "dHdt_Max_Terms": "16", "dHdt_Max_Parts": "6", "Max_Order_Of_T": "2",
+              "Num_Of_Coeffs_From_Params": "37", "Abort_RANSAC_by_Good_Sol": "false", "RANSAC_Dataset": "Synthetic", "Num_Of_Cores": "4",
+              "problem_print_out_name": "Trifocal Relative Pose Problem from Lines at Points"}
+    for k, v in expect.items():
+        assert lib.hcb200_settings_lookup(path, k.encode(), buf, 256) == 0 and buf.value.decode() == v, k
+    assert lib.hcb200_settings_lookup(path, b"No_Such_Key", buf, 256) == 1
+
+
+def test_count_solutions_follows_reference_definition():
+    tr = np.zeros((312, 31), np.complex64)
+    cv = np.zeros(312, np.uint8)
+    inf = np.zeros(312, np.uint8)
+    cv[[1, 2, 3]] = 1
+    inf[[3, 4]] = 1                       # converged AND infinity is possible
+    tr[2, 5] = 1 + 2e-4j                  # one variable off the real axis -> not "real"
+    tr[3, 7] = 1 + 1e-4j                  # exactly at the tolerance still counts (<=)
+    assert hc.count_solutions(tr, cv, inf, 1).tolist() == [[3, 2, 2]]

@@ -1,0 +1,212 @@
+"""CPU tests of the oracle (oracle/hc_oracle.c): internal consistency, and pinning against the REAL reference.
+
+The golden files under tests/golden/ were produced by tools/make_golden.py from the unmodified reference CPU-HC
+(oracle/_ref/libref_cpuhc.so, built from /root/reference with shim headers): its evaluators, LAPACK cgesv, and full
+path tracks.  The oracle is a different floating-point evaluation order of the same algorithm (explicit FMA placement,
+elimination with the U-solve folded in), so values are compared to rounding-level tolerances and integer counts to the
+noise floor the reference itself shows between LAPACK builds (SURVEY.md §7 "hard parts": 11098 vs 11088 vs 11071)."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# SURVEY.md App. C.3 — per-hypothesis (converged, inf, real) of the unmodified reference CPU-HC, hypotheses 0..5
+REF_C3_FIRST6 = [(129, 57, 6), (95, 79, 1), (133, 79, 6), (39, 72, 0), (140, 70, 9), (130, 72, 6)]
+
+
+def _pad_x(x30):
+    return np.concatenate([x30, [1.0]]).astype(np.complex64)
+
+
+def test_start_solutions_solve_start_system(oracle, problem):
+    """H(x_i; p_start) == 0 for all 312 start solutions (table interpretation check)."""
+    p = oracle.start_params
+    worst = 0.0
+    for i in range(312):
+        h = oracle.eval_H(_pad_x(problem["start_sols"][i]), p)
+        scale = max(1.0, float(np.abs(problem["start_sols"][i]).max()) ** 2)
+        worst = max(worst, float(np.abs(h).max()) / scale)
+    assert worst < 2e-5     # float32 evaluation of a degree-3 system
+
+
+def test_Hx_is_the_jacobian_of_H(oracle, problem):
+    rng = np.random.default_rng(1)
+    x = _pad_x(problem["start_sols"][17])
+    p = oracle.start_params
+    A = oracle.eval_Hx(x, p).astype(np.complex128)
+    eps = 1e-3
+    for col in rng.choice(30, size=8, replace=False):
+        xp, xm = x.copy(), x.copy()
+        xp[col] += eps
+        xm[col] -= eps
+        fd = (oracle.eval_H(xp, p).astype(np.complex128) - oracle.eval_H(xm, p).astype(np.complex128)) / (2 * eps)
+        assert np.allclose(A[:, col], fd, atol=2e-2 * max(1.0, np.abs(A[:, col]).max()), rtol=2e-2)
+
+
+def test_Ht_is_minus_dH_dt(oracle, problem, ransac0):
+    tgt, dif, _ = oracle.prepare_target_params(0, 1, ransac0["locations"], ransac0["tangents"])
+    x = _pad_x(problem["start_sols"][3])
+    t, eps = 0.4, 1e-3
+    b = oracle.eval_Ht(x, oracle.param_homotopy(t, tgt[0]), dif[0]).astype(np.complex128)
+    hp = oracle.eval_H(x, oracle.param_homotopy(t + eps, tgt[0])).astype(np.complex128)
+    hm = oracle.eval_H(x, oracle.param_homotopy(t - eps, tgt[0])).astype(np.complex128)
+    assert np.allclose(b, -(hp - hm) / (2 * eps), atol=5e-3 * max(1.0, np.abs(b).max()), rtol=5e-2)
+
+
+def test_evaluators_match_reference_golden(oracle):
+    g = np.load(os.path.join(GOLD, "ref_eval_vectors.npz"))
+    for k in range(g["x"].shape[0]):
+        x, p, dp = g["x"][k], g["p"][k], g["dp"][k]
+        for mine, ref in ((oracle.eval_Hx(x, p), g["Hx"][k]), (oracle.eval_H(x, p), g["H"][k]), (oracle.eval_Ht(x, p, dp), g["Ht"][k])):
+            scale = np.abs(ref).max()
+            # same terms, same order; only the FMA contraction differs (gcc contracts the reference's expressions freely)
+            assert np.abs(mine - ref).max() <= 4e-6 * scale
+        # structural zeros are exact zeros in both
+        assert np.array_equal(oracle.eval_Hx(x, p) == 0, g["Hx"][k] == 0)
+
+
+def test_solve_matches_lapack_golden_and_literal_lu(oracle):
+    g = np.load(os.path.join(GOLD, "ref_eval_vectors.npz"))
+    for k in range(g["x"].shape[0]):
+        A, b, ref = g["Hx"][k], g["Ht"][k], g["solve"][k]
+        exact = np.linalg.solve(A.astype(np.complex128), b.astype(np.complex128))
+        cond = np.linalg.cond(A.astype(np.complex128))
+        mine, info = oracle.solve(A, b)
+        lit, info2 = oracle.solve(A, b, lu_ref=True)
+        tol = 40 * cond * 6e-8
+        nrm = np.linalg.norm(exact)
+        assert info == 0 and info2 == 0
+        assert np.linalg.norm(mine - exact) / nrm < tol
+        assert np.linalg.norm(lit - exact) / nrm < tol
+        assert np.linalg.norm(ref - exact) / nrm < tol        # LAPACK is no closer to the truth than we are
+        assert np.linalg.norm(mine - ref) / nrm < 2 * tol
+
+
+def test_solve_pivot_rule_ties_and_singular(oracle):
+    # exact ties: the row that is FIRST in the current (virtually permuted) order must win -> identity solves exactly
+    A = np.eye(30, dtype=np.complex64)
+    b = (np.arange(30) + 1j).astype(np.complex64)
+    x, info = oracle.solve(A, b)
+    assert info == 0 and np.array_equal(x, b)
+    # column of equal magnitudes: rows 0 and 1 tie for pivot 0 -> row 0 (lowest position) is taken; result still exact
+    A = np.eye(30, dtype=np.complex64)
+    A[1, 0] = 1.0
+    x, info = oracle.solve(A, b)
+    assert info == 0 and np.allclose(A.astype(np.complex128) @ x, b, atol=1e-5)
+    # exactly singular: reported through info (k+1 of the first zero pivot), result not finite
+    A = np.eye(30, dtype=np.complex64)
+    A[7, 7] = 0
+    x, info = oracle.solve(A, b)
+    assert info == 8 and not np.all(np.isfinite(x))
+
+
+def test_hypothesis_sampler_known_answers(oracle, ransac0):
+    """glibc srand(0), rand() % 5117 -> (4481, 865, 961), (1853, 4061, 3216), ..."""
+    tgt, dif, picked = oracle.prepare_target_params(0, 5, ransac0["locations"], ransac0["tangents"])
+    assert picked.tolist() == [[4481, 865, 961], [1853, 4061, 3216], [241, 3873, 2374], [325, 1178, 1153], [2043, 1005, 1287]]
+    c1 = [-0.00808852445, 0.00629514595, -0.00956742745, -0.0355301499, 0.000342374929, 0.00298306812]
+    assert np.allclose(tgt[0, :6].real, c1, rtol=1e-6) and np.all(tgt[0].imag == 0)
+    assert tgt[0, 30:].tolist() == [1, 0.5, 1, 1]
+    assert np.array_equal(dif[0], (tgt[0] - oracle.start_params).astype(np.complex64))
+    g = np.load(os.path.join(GOLD, "ref_cpuhc_seed0_first6.npz"))
+    assert np.array_equal(tgt, g["target_params"][:5])          # the reference's own Prepare_Target_Params output
+
+
+@pytest.fixture(scope="module")
+def first6(oracle):
+    g = np.load(os.path.join(GOLD, "ref_cpuhc_seed0_first6.npz"))
+    tgt = g["target_params"]
+    dif = (tgt - oracle.start_params[None, :]).astype(np.complex64)
+    tr, cv, inf, st = oracle.track(tgt, dif, prune=False)
+    return g, tgt, tr, cv, inf, st
+
+
+def test_reference_golden_is_the_surveyed_reference():
+    from trifocal_pose_estimation_using_improved_gpuhc_b200 import hc
+    g = np.load(os.path.join(GOLD, "ref_cpuhc_seed0_first6.npz"))
+    assert [tuple(r) for r in hc.count_solutions(g["tracks"], g["converged"], g["infinity"], 6).tolist()] == REF_C3_FIRST6
+
+
+def test_tracker_vs_reference_cpuhc_first6(oracle, first6):
+    """Pruning off == the reference CPU-HC.  Flags are knife-edge float comparisons, so they are compared statistically:
+    the noise floor between two FP32 LU implementations is about one converged path per hypothesis."""
+    from trifocal_pose_estimation_using_improved_gpuhc_b200 import hc
+    g, tgt, tr, cv, inf, st = first6
+    mine = hc.count_solutions(tr, cv, inf, 6)
+    ref = np.array(REF_C3_FIRST6)
+    assert np.abs(mine[:, 0] - ref[:, 0]).max() <= 5          # converged per hypothesis
+    assert np.abs(mine[:, 1] - ref[:, 1]).max() <= 5          # infinity flags
+    assert np.abs(mine[:, 2] - ref[:, 2]).max() <= 2          # real solutions
+    assert abs(int(mine[:, 0].sum()) - int(ref[:, 0].sum())) <= 0.02 * ref[:, 0].sum()
+    assert (cv == g["converged"]).mean() > 0.97 and (inf == g["infinity"]).mean() > 0.97
+
+
+def test_endpoints_agree_after_newton_refinement(oracle, first6):
+    """north_star: converged solutions within 1e-4 relative after Newton refinement.  Both end points of every path that
+    converged in the oracle AND in the reference are polished in double precision against the target system."""
+    g, tgt, tr, cv, inf, st = first6
+    both = np.nonzero((cv == 1) & (g["converged"] == 1) & (inf == 0) & (g["infinity"] == 0))[0]
+    both = both[both < 2 * 312]          # hypotheses 0 and 1 keep the test fast
+    n_cmp, n_same = 0, 0
+    for pth in both:
+        h = pth // 312
+        xa, ra = oracle.newton_refine(tgt[h], tr[pth], iters=8)
+        xb, rb = oracle.newton_refine(tgt[h], g["tracks"][pth], iters=8)
+        if not (np.all(np.isfinite(xa)) and np.all(np.isfinite(xb))):
+            continue
+        n_cmp += 1
+        rel = np.abs(xa - xb).max() / max(1.0, np.abs(xb).max())
+        n_same += rel < 1e-4
+    assert n_cmp > 150
+    # a handful of paths jump to a neighbouring solution near singular points in one implementation and not the other
+    assert n_same >= 0.95 * n_cmp
+
+
+def test_gt_pose_is_found_and_scores_full_support(oracle, first6, ransac0):
+    """hypothesis 0 / track 104 is the ground-truth pose with 5117/5117 inliers in both view pairs."""
+    from trifocal_pose_estimation_using_improved_gpuhc_b200 import fixtures
+    g, tgt, tr, cv, inf, st = first6
+    assert cv[104] == 1 and g["converged"][104] == 1
+    ok, n21, n31, gate = oracle.score(tr[104], ransac0["locations"], ransac0["K"])
+    assert ok and gate and (n21, n31) == (5117, 5117)
+    ok_ref, r21, r31, _ = oracle.score(g["tracks"][104], ransac0["locations"], ransac0["K"])
+    assert ok_ref and (r21, r31) == (5117, 5117)
+    t21 = tr[104, 18:21].real
+    t21 = t21 / np.linalg.norm(t21)
+    gt = ransac0["gt_pose21"][3] / np.linalg.norm(ransac0["gt_pose21"][3])
+    assert abs(float(t21 @ gt) - 1.0) < 1e-3
+    # a non-solution fails the gate or the support test
+    ok_bad, *_ = oracle.score(tr[0], ransac0["locations"], ransac0["K"])
+    assert not ok_bad
+
+
+def test_pruning_only_removes_work(oracle, first6):
+    g, tgt, tr, cv, inf, st = first6
+    dif = (tgt[:1] - oracle.start_params[None, :]).astype(np.complex64)
+    trp, cvp, infp, stp = oracle.track(tgt[:1], dif, prune=True)
+    assert stp[:, 0].sum() < st[:312, 0].sum()
+    pruned = stp[:, 4] == 2
+    assert pruned.sum() > 100 and not np.any(cvp[pruned])
+    # a path that is not pruned follows exactly the same arithmetic as without pruning
+    same = ~pruned
+    assert np.array_equal(cvp[same], cv[:312][same])
+    assert np.array_equal(trp[same].view(np.uint64), tr[:312][same].view(np.uint64))
+
+
+def test_full_default_run_goldens_agree_with_reference_totals():
+    """Oracle golden (100 hypotheses, pruning off) vs the real reference's full run (tests/golden/ref_cpuhc_seed0_h100.npz)
+    and vs the numbers shipped in the reference repo (Output_Write_Files/CPU_Sols_Statistics.txt: 11098 521 6577)."""
+    o = np.load(os.path.join(GOLD, "oracle_seed0_h100_noprune.npz"))
+    r = np.load(os.path.join(GOLD, "ref_cpuhc_seed0_h100.npz"))
+    oc, rc = o["counts"], r["counts"]
+    assert rc.sum(0).tolist() == [11088, 6590, 514]            # SURVEY.md App. C.2 (this toolchain's LAPACK)
+    tot_o, tot_r = oc.sum(0), rc.sum(0)
+    assert abs(tot_o[0] - tot_r[0]) <= 0.01 * tot_r[0]         # converged
+    assert abs(tot_o[1] - tot_r[1]) <= 0.01 * tot_r[1]         # infinity
+    assert abs(tot_o[2] - tot_r[2]) <= 0.06 * tot_r[2]         # real (|imag| <= 1e-4 is the most fragile gate)
+    assert abs(tot_o[0] - 11098) <= 0.01 * 11098               # the authors' own CPU run
+    assert np.abs(oc[:, 0] - rc[:, 0]).max() <= 8 and np.abs(oc[:, 0] - rc[:, 0]).mean() < 2.5
+    same = (np.unpackbits(o["converged_bits"])[:31200] == np.unpackbits(r["converged_bits"])[:31200]).mean()
+    assert same > 0.975

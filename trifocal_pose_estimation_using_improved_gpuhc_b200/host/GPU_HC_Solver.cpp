@@ -1,0 +1,381 @@
+// See GPU_HC_Solver.hpp.  Flow of one round (same call order as the reference driver, cmd/magmaHC-main.cpp:32-66):
+//   ctor -> Allocate_Arrays -> Read_Problem_Data -> Read_RANSAC_Data(i) -> Prepare_Target_Params(seed)
+//        -> Set_RANSAC_Abort_Arrays -> Data_Transfer_From_Host_To_Device -> Set_CUDA_Stream_Attributes -> Solve_by_GPU_HC
+//        -> Free_Triplet_Edgels_Mem -> Free_Arrays_for_Aborting_RANSAC
+#include "GPU_HC_Solver.hpp"
+
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+using hcb200::complex32;
+
+#define HC_CUDA(call)                                                                                       \
+  do {                                                                                                      \
+    cudaError_t e_ = (call);                                                                                \
+    if (e_ != cudaSuccess) {                                                                                \
+      std::fprintf(stderr, "\033[1;31m[CUDA ERROR] %s:%d %s -> %s\033[0m\n", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      std::exit(2);          /* no CPU fallback: a failing device call is fatal (the reference only prints) */                     \
+    }                                                                                                       \
+  } while (0)
+
+static double wall_seconds()
+{ return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+GPU_HC_Solver::GPU_HC_Solver(YAML::Node cfg) : Problem_Setting_YAML_File(cfg)
+{
+  HC_problem                      = cfg["problem_name"].as<std::string>();
+  HC_print_problem_name           = cfg["problem_print_out_name"].as<std::string>();
+  GPUHC_Max_Steps                 = cfg["GPUHC_Max_Steps"].as<int>();
+  GPUHC_Max_Correction_Steps      = cfg["GPUHC_Max_Correction_Steps"].as<int>();
+  GPUHC_delta_t_incremental_steps = cfg["GPUHC_Num_Of_Steps_to_Increase_Delta_t"].as<int>();
+  Num_Of_Vars                     = cfg["Num_Of_Vars"].as<int>();
+  Num_Of_Params                   = cfg["Num_Of_Params"].as<int>();
+  Num_Of_Tracks                   = cfg["Num_Of_Tracks"].as<int>();
+  dHdx_Max_Terms                  = cfg["dHdx_Max_Terms"].as<int>();
+  dHdx_Max_Parts                  = cfg["dHdx_Max_Parts"].as<int>();
+  dHdt_Max_Terms                  = cfg["dHdt_Max_Terms"].as<int>();
+  dHdt_Max_Parts                  = cfg["dHdt_Max_Parts"].as<int>();
+  Abort_RANSAC_by_Good_Sol        = cfg["Abort_RANSAC_by_Good_Sol"].as<bool>();
+  RANSAC_Dataset_Name             = cfg["RANSAC_Dataset"].as<std::string>();
+  Num_Of_GPUs                     = cfg["Num_Of_GPUs"].as<int>();
+  // optional keys (not in the reference's file): iteration count (a macro there) and the tree root
+  num_ransac_iters                = cfg.as_or<int>("Num_Of_RANSAC_Iterations", NUM_OF_RANSAC_ITERATIONS);
+  const std::string root          = cfg.as_or<std::string>("Repo_Root", "../../");
+  verbose                         = cfg.as_or<bool>("Verbose", true);
+
+  if (HC_problem != "trifocal_2op1p_30x30" || Num_Of_Vars != HCB200_NUM_VARS || Num_Of_Params != HCB200_NUM_PARAMS ||
+      Num_Of_Tracks != HCB200_NUM_TRACKS) {
+    hcb200::log_error("this build has the trifocal_2op1p_30x30 system (30 vars, 33 params, 312 tracks) compiled in");
+    std::exit(1);
+  }
+
+  HC_CUDA(cudaGetDeviceCount(&device_count));
+  check_multiGPUs();
+  for (int g = 0; g < Num_Of_GPUs; g++) {
+    shard[g].device = device_of(g);
+    HC_CUDA(cudaSetDevice(shard[g].device));
+    cudaStream_t s; cudaEvent_t a, b;
+    HC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    HC_CUDA(cudaEventCreate(&a)); HC_CUDA(cudaEventCreate(&b));
+    shard[g].stream = s; shard[g].ev_start = a; shard[g].ev_stop = b;
+  }
+  int offset = 0;
+  for (int g = 0; g < Num_Of_GPUs; g++) {        // GPU_HC_Solver.cpp:85-88
+    sub_RANSAC_iters[g] = num_ransac_iters / Num_Of_GPUs + ((g < (num_ransac_iters % Num_Of_GPUs)) ? 1 : 0);
+    shard[g].path_offset = offset * Num_Of_Tracks;
+    offset += sub_RANSAC_iters[g];
+    if (verbose) std::printf("GPU %2d computes %2d RANSAC iterations\n", g, sub_RANSAC_iters[g]);
+  }
+  dHdx_Index_Size = Num_Of_Vars * Num_Of_Vars * dHdx_Max_Terms * dHdx_Max_Parts;
+  dHdt_Index_Size = Num_Of_Vars * dHdt_Max_Terms * dHdt_Max_Parts;
+
+  Problem_File_Path     = root + "problems/" + HC_problem;
+  RANSAC_Data_File_Path = root + "RANSAC_Data/" + HC_problem + "/" + RANSAC_Dataset_Name;
+  Write_Files_Path      = root + WRITE_FILES_FOLDER;
+  Evaluate_GPUHC_Sols = std::make_shared<Evaluations>(Write_Files_Path, "GPU-HC", Num_Of_Tracks, Num_Of_Vars);
+  Evaluate_GPUHC_Sols->Set_Num_Of_RANSAC_Iterations(num_ransac_iters);
+}
+
+void GPU_HC_Solver::check_multiGPUs()
+{
+  if (Num_Of_GPUs == 1 && verbose) hcb200::log_info("Only 1 GPU is used. Device ID = " + std::to_string(SET_GPU_DEVICE_ID));
+  if (Num_Of_GPUs < 1 || Num_Of_GPUs > MAX_NUM_OF_GPUS) {
+    hcb200::log_error("Requested GPUs larger than MAX_NUM_OF_GPUS");
+    std::printf("\033[1;31m[Requested GPUs] %d\t[Max GPUs] %d\033[0m\n", Num_Of_GPUs, MAX_NUM_OF_GPUS);
+    std::exit(1);
+  }
+  if (Num_Of_GPUs > device_count) {
+    hcb200::log_error("Not enough GPUs");
+    std::printf("\033[1;31m[Requested GPUs] %d\t[Available GPUs] %d\033[0m\n", Num_Of_GPUs, device_count);
+    std::exit(1);
+  }
+}
+
+void GPU_HC_Solver::Allocate_Arrays()
+{
+  const size_t V1 = Num_Of_Vars + 1, P1 = Num_Of_Params + 1, n_paths = (size_t)Num_Of_Paths();
+  h_Start_Sols   = (complex32*)std::malloc(sizeof(complex32) * Num_Of_Tracks * V1);
+  h_Start_Params = (complex32*)std::malloc(sizeof(complex32) * P1);
+  h_dHdx_Index = new int[dHdx_Index_Size];
+  h_dHdt_Index = new int[dHdt_Index_Size];
+  h_Camera_Intrinsic_Matrix = new float[9];
+  HC_CUDA(cudaMallocHost((void**)&h_GPU_HC_Track_Sols_Stack, sizeof(complex32) * n_paths * V1));
+  HC_CUDA(cudaMallocHost((void**)&h_is_GPU_HC_Sol_Converge_Stack, n_paths * sizeof(bool)));
+  HC_CUDA(cudaMallocHost((void**)&h_is_GPU_HC_Sol_Infinity_Stack, n_paths * sizeof(bool)));
+  for (int g = 0; g < Num_Of_GPUs; g++) {
+    DeviceShard& d = shard[g];
+    const size_t H = sub_RANSAC_iters[g], paths = H * Num_Of_Tracks;
+    HC_CUDA(cudaSetDevice(d.device));
+    HC_CUDA(cudaMallocHost((void**)&h_Target_Params[g], sizeof(complex32) * P1 * (H ? H : 1)));
+    HC_CUDA(cudaMallocHost((void**)&h_diffParams[g], sizeof(complex32) * P1 * (H ? H : 1)));
+    HC_CUDA(cudaMalloc((void**)&d.d_start_sols, sizeof(complex32) * Num_Of_Tracks * V1));
+    HC_CUDA(cudaMalloc((void**)&d.d_start_params, sizeof(complex32) * P1));
+    HC_CUDA(cudaMalloc((void**)&d.d_target, sizeof(complex32) * P1 * (H ? H : 1)));
+    HC_CUDA(cudaMalloc((void**)&d.d_diff, sizeof(complex32) * P1 * (H ? H : 1)));
+    HC_CUDA(cudaMalloc((void**)&d.d_tracks, sizeof(complex32) * V1 * (paths ? paths : 1)));
+    HC_CUDA(cudaMalloc((void**)&d.d_conv, paths ? paths : 1));
+    HC_CUDA(cudaMalloc((void**)&d.d_inf, paths ? paths : 1));
+    HC_CUDA(cudaMalloc(&d.d_ws, hcb200_workspace_bytes()));
+  }
+  arrays_allocated = true;
+}
+
+bool GPU_HC_Solver::Read_Problem_Data()
+{
+  Load_Problem_Data = std::make_shared<Data_Reader>(Problem_File_Path, RANSAC_Data_File_Path, Num_Of_Tracks, Num_Of_Vars, Num_Of_Params);
+  if (!Load_Problem_Data->Read_Start_Params(h_Start_Params)) { hcb200::log_error("Start Parameters not loaded successfully!"); return false; }
+  if (!Load_Problem_Data->Read_Start_Sols(h_Start_Sols)) { hcb200::log_error("Start Solutions not loaded successfully!"); return false; }
+  // The evaluation-index tables are part of the problem definition the reference ships; the device code was generated from
+  // them (codegen/gen_eval.py).  They are parsed here so a missing/short file is reported exactly like in the reference.
+  if (!Load_Problem_Data->Read_dHdx_Indices<int>(h_dHdx_Index)) { hcb200::log_error("dH/dx Evaluation Indices not loaded successfully!"); return false; }
+  if (!Load_Problem_Data->Read_dHdt_Indices<int>(h_dHdt_Index)) { hcb200::log_error("dH/dt Evaluation Indices not loaded successfully!"); return false; }
+  return true;
+}
+
+bool GPU_HC_Solver::Read_RANSAC_Data(int tp_index)
+{
+  Num_Of_Triplet_Edgels = Load_Problem_Data->get_Num_Of_Triplet_Edgels(tp_index);
+  if (Num_Of_Triplet_Edgels == 0) return false;
+  h_Triplet_Edge_Locations = new float[(size_t)Num_Of_Triplet_Edgels * 6];
+  h_Triplet_Edge_Tangents  = new float[(size_t)Num_Of_Triplet_Edgels * 6];
+  edgels_allocated = true;
+  if (!Load_Problem_Data->Read_Camera_Poses(h_Camera_Pose21, h_Camera_Pose31, tp_index)) { hcb200::log_error("Camera Extrinsic Matrices not loaded successfully!"); return false; }
+  if (!Load_Problem_Data->Read_Intrinsic_Matrix(h_Camera_Intrinsic_Matrix)) { hcb200::log_error("Camera Intrinsic Matrices not loaded successfully!"); return false; }
+  Load_Problem_Data->Read_Triplet_Edgels(h_Triplet_Edge_Locations, h_Triplet_Edge_Tangents);
+  return true;
+}
+
+// Hypothesis sampling + target parameters (reference GPU_HC_Solver.cpp:252-306): ONE rand() stream consumed in GPU-major
+// order, so the hypothesis sequence does not depend on Num_Of_GPUs.  Parameter layout: SURVEY.md App. A.2.
+void GPU_HC_Solver::Prepare_Target_Params(unsigned rand_seed_)
+{
+  std::srand(rand_seed_);
+  const int P1 = Num_Of_Params + 1;
+  for (int g = 0; g < Num_Of_GPUs; g++) {
+    for (int ti = 0; ti < sub_RANSAC_iters[g]; ti++) {
+      unsigned e[3];
+      do { for (int r = 0; r < 3; r++) e[r] = std::rand() % Num_Of_Triplet_Edgels; }
+      while (!(e[0] != e[1] && e[1] != e[2]));          // the reference never tests e0 != e2
+      complex32* T = h_Target_Params[g] + (size_t)ti * P1;
+      complex32* D = h_diffParams[g] + (size_t)ti * P1;
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 6; j++) T[i * 6 + j] = hcb200::make_c32(h_Triplet_Edge_Locations[(size_t)e[i] * 6 + j], 0.0f);
+      for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 6; j++) T[18 + i * 6 + j] = hcb200::make_c32(h_Triplet_Edge_Tangents[(size_t)e[i] * 6 + j], 0.0f);
+      T[30] = hcb200::make_c32(1.0f, 0.0f);
+      T[31] = hcb200::make_c32(0.5f, 0.0f);
+      T[32] = hcb200::make_c32(1.0f, 0.0f);
+      T[33] = hcb200::make_c32(1.0f, 0.0f);
+      for (int i = 0; i < P1; i++) D[i] = hcb200::make_c32(T[i].x - h_Start_Params[i].x, T[i].y - h_Start_Params[i].y);
+    }
+  }
+}
+
+void GPU_HC_Solver::Set_RANSAC_Abort_Arrays()
+{
+  if (!Abort_RANSAC_by_Good_Sol) return;
+  for (int g = 0; g < Num_Of_GPUs; g++) {
+    DeviceShard& d = shard[g];
+    const size_t paths = (size_t)sub_RANSAC_iters[g] * Num_Of_Tracks;
+    HC_CUDA(cudaSetDevice(d.device));
+    h_Found_Trifocal_Sols[g] = new bool[1];
+    h_Found_Trifocal_Sols[g][0] = false;
+    h_Trifocal_Sols_Batch_Index[g] = new int[paths ? paths : 1];
+    for (size_t i = 0; i < paths; i++) h_Trifocal_Sols_Batch_Index[g][i] = -1;
+    h_best[g] = new hcb200_best_record();
+    HC_CUDA(cudaMalloc((void**)&d.d_K, 9 * sizeof(float)));
+    HC_CUDA(cudaMalloc((void**)&d.d_edgels, (size_t)Num_Of_Triplet_Edgels * 6 * sizeof(float)));
+    HC_CUDA(cudaMalloc((void**)&d.d_found, sizeof(bool)));
+    HC_CUDA(cudaMalloc((void**)&d.d_found_index, (paths ? paths : 1) * sizeof(int)));
+    HC_CUDA(cudaMalloc((void**)&d.d_best, sizeof(hcb200_best_record)));
+  }
+  abort_arrays_allocated = true;
+}
+
+void GPU_HC_Solver::Data_Transfer_From_Host_To_Device()
+{
+  const size_t V1 = Num_Of_Vars + 1, P1 = Num_Of_Params + 1;
+  for (int g = 0; g < Num_Of_GPUs; g++) {
+    DeviceShard& d = shard[g];
+    const size_t H = sub_RANSAC_iters[g], paths = H * Num_Of_Tracks;
+    cudaStream_t s = (cudaStream_t)d.stream;
+    HC_CUDA(cudaSetDevice(d.device));
+    const double t0 = wall_seconds();
+    HC_CUDA(cudaMemcpyAsync(d.d_start_sols, h_Start_Sols, sizeof(complex32) * Num_Of_Tracks * V1, cudaMemcpyHostToDevice, s));
+    HC_CUDA(cudaMemcpyAsync(d.d_start_params, h_Start_Params, sizeof(complex32) * P1, cudaMemcpyHostToDevice, s));
+    if (H) {
+      HC_CUDA(cudaMemcpyAsync(d.d_target, h_Target_Params[g], sizeof(complex32) * P1 * H, cudaMemcpyHostToDevice, s));
+      HC_CUDA(cudaMemcpyAsync(d.d_diff, h_diffParams[g], sizeof(complex32) * P1 * H, cudaMemcpyHostToDevice, s));
+    }
+    if (Abort_RANSAC_by_Good_Sol) {
+      HC_CUDA(cudaMemcpyAsync(d.d_edgels, h_Triplet_Edge_Locations, (size_t)Num_Of_Triplet_Edgels * 6 * sizeof(float), cudaMemcpyHostToDevice, s));
+      HC_CUDA(cudaMemcpyAsync(d.d_K, h_Camera_Intrinsic_Matrix, 9 * sizeof(float), cudaMemcpyHostToDevice, s));
+      if (paths) HC_CUDA(cudaMemcpyAsync(d.d_found_index, h_Trifocal_Sols_Batch_Index[g], paths * sizeof(int), cudaMemcpyHostToDevice, s));
+      HC_CUDA(cudaMemcpyAsync(d.d_found, h_Found_Trifocal_Sols[g], sizeof(bool), cudaMemcpyHostToDevice, s));
+    }
+    HC_CUDA(cudaStreamSynchronize(s));
+    transfer_h2d_time[g] = wall_seconds() - t0;
+  }
+}
+
+// The reference pins its 152 KB index table in L2 here (GPU_HC_Solver.cpp:364-378).  There is no table any more: the
+// operand words live in shared memory and the system is compiled in, so nothing needs a persisting window.
+void GPU_HC_Solver::Set_CUDA_Stream_Attributes() {}
+
+void GPU_HC_Solver::Solve_by_GPU_HC()
+{
+  if (verbose) std::cout << "GPU computing ..." << std::endl << std::endl;
+  const unsigned flags = prune_paths ? HCB200_FLAG_PRUNE_PATHS : 0u;
+  const size_t V1 = Num_Of_Vars + 1;
+
+  multi_GPUs_time = wall_seconds();
+  for (int g = 0; g < Num_Of_GPUs; g++) {               // one asynchronous launch per GPU (GPU_HC_Solver.cpp:390-436)
+    DeviceShard& d = shard[g];
+    if (!sub_RANSAC_iters[g]) continue;
+    HC_CUDA(cudaSetDevice(d.device));
+    HC_CUDA(cudaEventRecord((cudaEvent_t)d.ev_start, (cudaStream_t)d.stream));
+    int rc;
+    if (Abort_RANSAC_by_Good_Sol)
+      rc = hcb200_track_abort(d.stream, sub_RANSAC_iters[g], Num_Of_Triplet_Edgels, GPUHC_Max_Steps, GPUHC_Max_Correction_Steps,
+                              GPUHC_delta_t_incremental_steps, flags, d.d_start_sols, d.d_start_params, d.d_target, d.d_diff,
+                              d.d_edgels, d.d_K, d.d_tracks, d.d_conv, d.d_inf, d.d_found, d.d_found_index, d.d_best, nullptr, d.d_ws);
+    else
+      rc = hcb200_track(d.stream, sub_RANSAC_iters[g], GPUHC_Max_Steps, GPUHC_Max_Correction_Steps, GPUHC_delta_t_incremental_steps,
+                        flags, d.d_start_sols, d.d_start_params, d.d_target, d.d_diff, d.d_tracks, d.d_conv, d.d_inf, nullptr, d.d_ws);
+    if (rc != 0) { std::fprintf(stderr, "[ERROR] tracker launch failed on GPU %d: %s\n", g, hcb200_error_string(rc)); std::exit(2); }
+    HC_CUDA(cudaEventRecord((cudaEvent_t)d.ev_stop, (cudaStream_t)d.stream));
+  }
+  for (int g = 0; g < Num_Of_GPUs; g++) {               // GPU_HC_Solver.cpp:440-444
+    HC_CUDA(cudaSetDevice(shard[g].device));
+    HC_CUDA(cudaStreamSynchronize((cudaStream_t)shard[g].stream));
+  }
+  multi_GPUs_time = wall_seconds() - multi_GPUs_time;
+
+  // results: every GPU copies straight into its slice of the stacked host arrays (reference: per-GPU copies + memcpy, :449-506)
+  for (int g = 0; g < Num_Of_GPUs; g++) {
+    DeviceShard& d = shard[g];
+    const size_t paths = (size_t)sub_RANSAC_iters[g] * Num_Of_Tracks;
+    if (!paths) continue;
+    cudaStream_t s = (cudaStream_t)d.stream;
+    HC_CUDA(cudaSetDevice(d.device));
+    float ms = 0.f;
+    HC_CUDA(cudaEventElapsedTime(&ms, (cudaEvent_t)d.ev_start, (cudaEvent_t)d.ev_stop));
+    gpu_time[g] = ms * 1e-3;
+    const double t0 = wall_seconds();
+    HC_CUDA(cudaMemcpyAsync(h_GPU_HC_Track_Sols_Stack + (size_t)d.path_offset * V1, d.d_tracks, sizeof(complex32) * V1 * paths, cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaMemcpyAsync(h_is_GPU_HC_Sol_Converge_Stack + d.path_offset, d.d_conv, paths, cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaMemcpyAsync(h_is_GPU_HC_Sol_Infinity_Stack + d.path_offset, d.d_inf, paths, cudaMemcpyDeviceToHost, s));
+    if (Abort_RANSAC_by_Good_Sol) {
+      HC_CUDA(cudaMemcpyAsync(h_Found_Trifocal_Sols[g], d.d_found, sizeof(bool), cudaMemcpyDeviceToHost, s));
+      HC_CUDA(cudaMemcpyAsync(h_Trifocal_Sols_Batch_Index[g], d.d_found_index, paths * sizeof(int), cudaMemcpyDeviceToHost, s));
+      HC_CUDA(cudaMemcpyAsync(h_best[g], d.d_best, sizeof(hcb200_best_record), cudaMemcpyDeviceToHost, s));
+    }
+    HC_CUDA(cudaStreamSynchronize(s));
+    transfer_d2h_time[g] = wall_seconds() - t0;
+  }
+
+  // tiny gather: the best record of every GPU, reduced on the host (smallest global path id wins)
+  found_path_ids.clear();
+  best_record = hcb200_best_record();
+  best_record.path_id = -1;
+  if (Abort_RANSAC_by_Good_Sol) {
+    for (int g = 0; g < Num_Of_GPUs; g++) {
+      const size_t paths = (size_t)sub_RANSAC_iters[g] * Num_Of_Tracks;
+      if (!paths) continue;
+      for (size_t i = 0; i < paths; i++)
+        if (h_Trifocal_Sols_Batch_Index[g][i] != -1) found_path_ids.push_back(shard[g].path_offset + h_Trifocal_Sols_Batch_Index[g][i]);
+      if (h_best[g]->found && (!best_record.found || shard[g].path_offset + h_best[g]->path_id < best_record.path_id)) {
+        best_record = *h_best[g];
+        best_record.path_id += shard[g].path_offset;
+      }
+      best_record.n_passed = (int)found_path_ids.size();
+    }
+  }
+
+  if (verbose) {
+    std::cout << "---------------------------------------------------------------------------------" << std::endl;
+    std::cout << "## Solving " << HC_print_problem_name << std::endl << std::endl;
+    std::printf("## Timings:\n - GPU Computation Time = %7.2f (ms)\n", multi_GPUs_time * 1000);
+  }
+
+  Evaluate_GPUHC_Sols->Evaluate_RANSAC_HC_Sols(h_GPU_HC_Track_Sols_Stack, h_is_GPU_HC_Sol_Converge_Stack, h_is_GPU_HC_Sol_Infinity_Stack);
+  per_hypothesis_counts = Evaluate_GPUHC_Sols->Per_Hypothesis_Counts;
+  if (verbose) {
+    std::cout << "\n## Evaluation of GPU-HC Solutions: " << std::endl;
+    std::cout << " - Number of Converged Solutions:       " << Evaluate_GPUHC_Sols->Num_Of_Coverged_Sols << std::endl;
+    std::cout << " - Number of Real Solutions:            " << Evaluate_GPUHC_Sols->Num_Of_Real_Sols << std::endl;
+    std::cout << " - Number of Infinity Failed Solutions: " << Evaluate_GPUHC_Sols->Num_Of_Inf_Sols << std::endl;
+  }
+  Collect_Num_Of_Coverged_Sols.push_back(Evaluate_GPUHC_Sols->Num_Of_Coverged_Sols);
+  Collect_Num_Of_Inf_Sols.push_back(Evaluate_GPUHC_Sols->Num_Of_Inf_Sols);
+  Collect_Num_Of_Real_Sols.push_back(Evaluate_GPUHC_Sols->Num_Of_Real_Sols);
+
+  Evaluate_GPUHC_Sols->Transform_GPUHC_Sols_to_Trifocal_Relative_Pose(h_GPU_HC_Track_Sols_Stack, h_is_GPU_HC_Sol_Converge_Stack, h_Camera_Intrinsic_Matrix);
+  found_pose = Evaluate_GPUHC_Sols->get_Solution_with_Maximal_Support(Num_Of_Triplet_Edgels, h_Triplet_Edge_Locations, h_Triplet_Edge_Tangents, h_Camera_Intrinsic_Matrix);
+  pose_residuals = {100.f, 100.f, 100.f, 100.f};
+  if (found_pose) {
+    Evaluate_GPUHC_Sols->Measure_Relative_Pose_Error(h_Camera_Pose21, h_Camera_Pose31);
+    pose_residuals = {Evaluate_GPUHC_Sols->Min_Residual_R21, Evaluate_GPUHC_Sols->Min_Residual_R31,
+                      Evaluate_GPUHC_Sols->Min_Residual_t21, Evaluate_GPUHC_Sols->Min_Residual_t31};
+    if (verbose) {
+      std::printf("## Pose with maximal support: path %d, inliers (1,2) %u / (1,3) %u of %d\n", Evaluate_GPUHC_Sols->Best_Candidate_Path_Index,
+                  Evaluate_GPUHC_Sols->Max_Num_Of_Reproj_Inliers_Views21, Evaluate_GPUHC_Sols->Max_Num_Of_Reproj_Inliers_Views31, Num_Of_Triplet_Edgels);
+      std::printf(" - residuals vs GT: R21 %.3g rad, R31 %.3g rad, t21 %.3g, t31 %.3g%s\n", pose_residuals[0], pose_residuals[1],
+                  pose_residuals[2], pose_residuals[3], Evaluate_GPUHC_Sols->success_flag ? "   ### Found GT pose!" : "");
+    }
+  }
+  Evaluate_GPUHC_Sols->Flush_Out_Data();
+}
+
+void GPU_HC_Solver::Export_Data() {}
+
+void GPU_HC_Solver::Free_Arrays_for_Aborting_RANSAC()
+{
+  if (!abort_arrays_allocated) return;
+  for (int g = 0; g < Num_Of_GPUs; g++) {
+    DeviceShard& d = shard[g];
+    HC_CUDA(cudaSetDevice(d.device));
+    delete[] h_Found_Trifocal_Sols[g]; h_Found_Trifocal_Sols[g] = nullptr;
+    delete[] h_Trifocal_Sols_Batch_Index[g]; h_Trifocal_Sols_Batch_Index[g] = nullptr;
+    delete h_best[g]; h_best[g] = nullptr;
+    cudaFree(d.d_edgels); cudaFree(d.d_found); cudaFree(d.d_found_index); cudaFree(d.d_K); cudaFree(d.d_best);
+    d.d_edgels = d.d_K = nullptr; d.d_found = nullptr; d.d_found_index = nullptr; d.d_best = nullptr;
+  }
+  abort_arrays_allocated = false;
+}
+
+void GPU_HC_Solver::Free_Triplet_Edgels_Mem()
+{
+  if (!edgels_allocated) return;
+  delete[] h_Triplet_Edge_Locations; delete[] h_Triplet_Edge_Tangents;
+  h_Triplet_Edge_Locations = h_Triplet_Edge_Tangents = nullptr;
+  edgels_allocated = false;
+}
+
+GPU_HC_Solver::~GPU_HC_Solver()
+{
+  Free_Arrays_for_Aborting_RANSAC();
+  Free_Triplet_Edgels_Mem();
+  for (int g = 0; g < Num_Of_GPUs && g < MAX_NUM_OF_GPUS; g++) {
+    DeviceShard& d = shard[g];
+    if (!d.stream) continue;
+    cudaSetDevice(d.device);
+    if (arrays_allocated) {
+      cudaFree(d.d_start_sols); cudaFree(d.d_start_params); cudaFree(d.d_target); cudaFree(d.d_diff); cudaFree(d.d_tracks);
+      cudaFree(d.d_conv); cudaFree(d.d_inf); cudaFree(d.d_ws);
+      cudaFreeHost(h_Target_Params[g]); cudaFreeHost(h_diffParams[g]);
+    }
+    cudaEventDestroy((cudaEvent_t)d.ev_start); cudaEventDestroy((cudaEvent_t)d.ev_stop);
+    cudaStreamDestroy((cudaStream_t)d.stream);
+  }
+  if (arrays_allocated) {
+    std::free(h_Start_Sols); std::free(h_Start_Params);
+    delete[] h_dHdx_Index; delete[] h_dHdt_Index; delete[] h_Camera_Intrinsic_Matrix;
+    cudaFreeHost(h_GPU_HC_Track_Sols_Stack); cudaFreeHost(h_is_GPU_HC_Sol_Converge_Stack); cudaFreeHost(h_is_GPU_HC_Sol_Infinity_Stack);
+  }
+}

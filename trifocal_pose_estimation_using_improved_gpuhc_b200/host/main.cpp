@@ -1,0 +1,89 @@
+// hc-main — command-line driver, same usage and output files as the reference executable
+// (cmd/magmaHC-main.cpp:197-260):   ./hc-main -p trifocal_2op1p_30x30        (run from <root>/build/bin, or add -d <root>)
+// It runs the GPU solver only: the reference's CPU-HC half is its baseline, not part of this product (no CPU fallback).
+// Files written under <root>/Output_Write_Files/: GPU_Timings.txt (ms per round), GPU_Sols_Statistics.txt
+// (converged <TAB> real <TAB> infinity per round) — SURVEY.md App. A.4.
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "GPU_HC_Solver.hpp"
+
+static void print_help()
+{
+  std::printf("Usage: ./hc-main [options]\n\noptions:\n"
+              "  -h, --help            show this help message and exit\n"
+              "  -p, --problem NAME    problem folder name under <root>/problems (trifocal_2op1p_30x30)\n"
+              "  -d, --directory ROOT  repository root holding problems/, RANSAC_Data/, Output_Write_Files/ (default ../../)\n"
+              "  -s, --set KEY=VALUE   override one settings key (repeatable)\n");
+}
+
+static bool run_GPU_HC_Solver(YAML::Node settings, const std::string& root)
+{
+  std::vector<double> all_ms;
+  GPU_HC_Solver GPU_HC_(settings);
+  GPU_HC_.Allocate_Arrays();
+  for (int ti = 0; ti < TEST_RANSAC_TIMES; ti++) {
+    if (!GPU_HC_.Read_Problem_Data()) return false;
+    if (!GPU_HC_.Read_RANSAC_Data(ti)) return false;
+    GPU_HC_.Prepare_Target_Params(ti);
+    GPU_HC_.Set_RANSAC_Abort_Arrays();
+    GPU_HC_.Data_Transfer_From_Host_To_Device();
+    GPU_HC_.Set_CUDA_Stream_Attributes();
+    GPU_HC_.Solve_by_GPU_HC();
+    GPU_HC_.Free_Triplet_Edgels_Mem();
+    GPU_HC_.Free_Arrays_for_Aborting_RANSAC();
+    all_ms.push_back(GPU_HC_.multi_GPUs_time * 1000);
+  }
+  double avg = 0, mx = 0, mn = 1e30, var = 0;
+  for (double v : all_ms) { avg += v; mx = std::max(mx, v); mn = std::min(mn, v); }
+  avg /= all_ms.size();
+  for (double v : all_ms) var += (v - avg) * (v - avg);
+  std::printf("\n## Running %d rounds of %d RANSAC iterations:\n", TEST_RANSAC_TIMES, GPU_HC_.Num_Of_RANSAC_Iterations());
+  std::printf(" - [Average GPU Computation Time] %7.2f (ms)\n - [Maximal GPU Computation Time] %7.2f (ms)\n"
+              " - [Minimal GPU Computation Time] %7.2f (ms)\n - [Std dev GPU Computation Time] %7.2f (ms)\n",
+              avg, mx, mn, std::sqrt(var / all_ms.size()));
+
+  const std::string out_dir = root + WRITE_FILES_FOLDER;
+  std::ofstream timings(out_dir + "GPU_Timings.txt");
+  if (!timings.is_open()) hcb200::log_file_error(out_dir + "GPU_Timings.txt");
+  for (double v : all_ms) timings << v << "\n";
+  std::ofstream stats(out_dir + "GPU_Sols_Statistics.txt");
+  if (!stats.is_open()) hcb200::log_file_error(out_dir + "GPU_Sols_Statistics.txt");
+  for (size_t i = 0; i < all_ms.size(); i++)
+    stats << GPU_HC_.Collect_Num_Of_Coverged_Sols[i] << "\t" << GPU_HC_.Collect_Num_Of_Real_Sols[i] << "\t" << GPU_HC_.Collect_Num_Of_Inf_Sols[i] << "\n";
+  return true;
+}
+
+int main(int argc, char** argv)
+{
+  std::string problem, root = "../../";
+  std::vector<std::string> sets;
+  if (argc < 2) { print_help(); return 0; }
+  for (int i = 1; i < argc; i++) {
+    const std::string a = argv[i];
+    if (a == "-h" || a == "--help") { print_help(); return 0; }
+    else if ((a == "-p" || a == "--problem") && i + 1 < argc) problem = argv[++i];
+    else if ((a == "-d" || a == "--directory") && i + 1 < argc) { root = argv[++i]; if (root.back() != '/') root += '/'; }
+    else if ((a == "-s" || a == "--set") && i + 1 < argc) sets.push_back(argv[++i]);
+    else { hcb200::log_error("Invalid input arguments!"); print_help(); return 0; }
+  }
+  if (problem.empty()) { hcb200::log_error("Invalid input arguments!"); print_help(); return 0; }
+  YAML::Node settings;
+  try {
+    settings = YAML::LoadFile(root + "problems/" + problem + "/gpuhc_settings.yaml");
+    settings.set("Repo_Root", root);
+    for (const auto& kv : sets) {
+      const size_t eq = kv.find('=');
+      if (eq != std::string::npos) settings.set(YAML::strip(kv.substr(0, eq)), YAML::strip(kv.substr(eq + 1)));
+    }
+    std::cout << std::endl << settings << std::endl;
+  } catch (const std::exception& e) {
+    std::cerr << "Exception: " << e.what() << std::endl;
+    return 0;
+  }
+  return run_GPU_HC_Solver(settings, root) ? 0 : 1;
+}
