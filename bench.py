@@ -160,6 +160,33 @@ def cpu_baseline_leg(sample_hyp):
                       % (sample_hyp, sample_hyp * 312, cores)}
 
 
+def ref_gpu_leg(prob, rs, target, diff, H, abort):
+    """The reference's own GPU-HC++ kernel (unmodified sources compiled for sm_100a with a MAGMA shim) on the
+    same round, same GPU, timed launch->sync with CUDA events like multi_GPUs_time; tracks are re-loaded outside the timing."""
+    import torch
+    from oracle import pyoracle
+    if not os.path.exists(pyoracle.REF_GPU_SO):
+        return None
+    ref = pyoracle.ReferenceGPU(prob, device="cuda:%d" % torch.cuda.current_device())
+    ref.setup(target, diff, rs["locations"], rs["K"])
+    ts = []
+    for i in range(5):
+        ref.reload()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ref.track_abort() if abort else ref.track()
+        b.record()
+        b.synchronize()
+        if i >= 2:
+            ts.append(a.elapsed_time(b))
+    tr, cv, inf = ref.results()
+    ms = float(np.mean(ts))
+    return {"what": "reference GPU-HC++ kernel (…TrunPaths%s.cu) built for sm_100a, same inputs" % ("_TrunRANSAC" if abort else ""),
+            "ms_per_step": ms, "value": H / (ms * 1e-3), "unit": "hypotheses/s",
+            "result": {"converged": int(cv.sum()), "infinity": int(inf.sum())}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,6 +198,7 @@ def main():
     ap.add_argument("--no-prune", action="store_true")
     ap.add_argument("--ref-hyp", type=int, default=8, help="hypotheses per step of the reference CPU arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference GPU-HC++ kernels (oracle/_ref/libref_gpuhc.so)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -319,6 +347,11 @@ def main():
                          "stages_per_path": float(stats[:, 1].sum() + stats[:, 2].sum()) / n_paths},
             "result": {"converged": int(counts[:, 0].sum()), "infinity": int(counts[:, 1].sum()), "real": int(counts[:, 2].sum())},
         }
+        if world == 1 and not args.no_ref_gpu:
+            rg = ref_gpu_leg(prob, rs, target, diff, H, args.abort)
+            if rg:
+                rg["speedup_ours_vs_ref_gpu"] = rg["ms_per_step"] / ms_per_step
+                line["ref_gpu"] = rg
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_leg(args.ref_hyp)
         print(json.dumps(line))
