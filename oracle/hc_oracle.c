@@ -121,15 +121,21 @@ void hco_eval_Ht(const int* dHdt, const hco_c32* x, const hco_c32* p, const hco_
 
 /* ------------------------------------------------------------------------------------------------------------
  * linear solve — the spec.
- * Same pivot rule as dev-cgesv-batched-small.cuh:55-81 (key |re|+|im|, first maximum in CURRENT row order wins,
- * virtual row exchange through `pos`), same multipliers (row entry times the pivot's reciprocal, :84-86) and the
- * same rank-1 updates (:87-93).  The only re-organisation: rows that were already pivoted are swept too
- * (Gauss-Jordan), which performs the U-solve (:97-106) inside the same 30 steps; x_k = b_pivot(k) * (1/pivot_k). */
+ * Partial-pivot elimination in natural column order with the pivot key of dev-cgesv-batched-small.cuh:55-65 (|re|+|im|),
+ * multipliers = row entry times the pivot's reciprocal (:84-86) and the same rank-1 updates (:87-93), re-organised as
+ * Gauss-Jordan: rows that were already pivoted are swept too, which performs the U-solve (:97-106) inside the same 30
+ * steps; x_k = b_pivot(k) * (1/pivot_k).  Three rules make the result independent of HOW a (block-parallel) implementation
+ * schedules the steps:
+ *   - ties of the pivot key are broken by the lowest ROW index (the reference takes the first maximum in its current,
+ *     virtually permuted row order, :57-65 — same set of maxima, different member in the rare exact-tie case);
+ *   - a row whose entry in the pivot column is exactly zero is not touched (its multiplier would be 0);
+ *   - a pivot column whose candidates are all exactly zero makes the system singular: every component of the result is NaN
+ *     (the reference continues with a multiplier of 1 and later divides by the zero diagonal, :66-68,100). */
 int hco_solve(hco_c32* A, hco_c32* b)
 {
-  int pos[HCO_N], done[HCO_N], piv[HCO_N], info = 0;
+  int done[HCO_N], piv[HCO_N];
   hco_c32 rsave[HCO_N];
-  for (int i = 0; i < HCO_N; i++) { pos[i] = i; done[i] = 0; }
+  for (int i = 0; i < HCO_N; i++) done[i] = 0;
   for (int k = 0; k < HCO_N; k++) {
     uint32_t maxbits = 0;
     uint32_t key[HCO_N];
@@ -137,17 +143,19 @@ int hco_solve(hco_c32* A, hco_c32* b)
       key[i] = done[i] ? 0u : key_bits(fabsf(A[i * HCO_N + k].re) + fabsf(A[i * HCO_N + k].im));
       if (key[i] > maxbits) maxbits = key[i];
     }
-    int p = -1, ppos = 1 << 30, q = -1;
-    for (int i = 0; i < HCO_N; i++) {
-      if (!done[i] && key[i] == maxbits && pos[i] < ppos) { p = i; ppos = pos[i]; }
-      if (pos[i] == k) q = i;
+    if (maxbits == 0) {
+      for (int i = 0; i < HCO_N; i++) b[i] = c_make(NAN, NAN);
+      return k + 1;
     }
-    pos[q] = pos[p]; pos[p] = k; done[p] = 1; piv[k] = p;
-    if (maxbits == 0 && info == 0) info = k + 1;
+    int p = -1;
+    for (int i = 0; i < HCO_N && p < 0; i++)
+      if (!done[i] && key[i] == maxbits) p = i;
+    done[p] = 1; piv[k] = p;
     const hco_c32 r = c_recip(A[p * HCO_N + k]);
     rsave[p] = r;
     for (int i = 0; i < HCO_N; i++) {
       if (i == p) continue;
+      if (A[i * HCO_N + k].re == 0.0f && A[i * HCO_N + k].im == 0.0f) continue;
       const hco_c32 m = c_mul(A[i * HCO_N + k], r);
       for (int j = k + 1; j < HCO_N; j++)
         A[i * HCO_N + j] = c_msub(A[i * HCO_N + j], m, A[p * HCO_N + j]);
@@ -157,7 +165,7 @@ int hco_solve(hco_c32* A, hco_c32* b)
   hco_c32 x[HCO_N];
   for (int k = 0; k < HCO_N; k++) x[k] = c_mul(b[piv[k]], rsave[piv[k]]);
   memcpy(b, x, sizeof x);
-  return info;
+  return 0;
 }
 
 /* Literal operation order of cgesv_batched_small_device<30> (dev-cgesv-batched-small.cuh:38-107), kept to show that

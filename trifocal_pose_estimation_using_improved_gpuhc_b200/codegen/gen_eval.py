@@ -19,6 +19,14 @@ What we emit instead (same arithmetic per term, see "evaluation spec" in DESIGN.
   * per-lane operands are one packed 32-bit word per slot:  cq byte offset | x_d<<10 | x_e<<15 | x_f<<20.
 Term order inside every matrix entry is the table order, so sums are bit-identical to the oracle's
 table-driven evaluation (`oracle/hc_oracle.c`).
+
+Block structure of the Jacobian (`analyze_blocks`).  A symbolic partial-pivoting elimination in natural column order shows
+that the first K1 = 18 pivot steps never couple more than six rows: the rows fall into independent groups (here four 6-row
+blocks and two 3-row blocks) whose "sparse" columns are private to the group, and only columns 18..29 are shared.  Steps
+of different groups commute exactly, so the kernel runs them side by side ("super-steps": 5 instead of 18 sequential
+steps) and keeps, per row, only the group's <= 5 sparse columns plus the 12 dense ones (17 register slots instead of 30).
+The generator assigns every group a 6-lane segment (two 3-row groups share one), rows ascending inside a segment, and emits
+the lane permutation, the per-lane slot maps and the scatter of the evaluated entries into slots.
 """
 import os
 import sys
@@ -95,6 +103,64 @@ def schedule(seqs):
     return [[q[k] if k < len(q) else None for q in seqs] for k in range(n)]
 
 
+def analyze_blocks(hx_terms):
+    """Symbolic elimination -> (K1, segments, seg_cols).  segments[g] = sorted rows (<= 6), seg_cols[g] = the segment's
+    private pivot columns in natural order; columns K1..N-1 are dense (shared by all rows)."""
+    P = np.zeros((N, N), bool)
+    for (r, c) in hx_terms:
+        P[r, c] = True
+    parent = list(range(N))
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    cand_of = []
+    K1 = N
+    for k in range(N):
+        cand = [r for r in range(N) if P[r, k]]
+        if len(cand) > 6:
+            K1 = k
+            break
+        cand_of.append(cand)
+        u = np.zeros(N, bool)
+        for r in cand:
+            u |= P[r]
+        u[:k + 1] = False
+        for r in cand:
+            P[r] |= u
+        for r in cand[1:]:
+            parent[find(r)] = find(cand[0])
+    comps = {}
+    for r in range(N):
+        comps.setdefault(find(r), []).append(r)
+    comps = sorted(comps.values(), key=lambda rows: min(k for k in range(K1) if set(cand_of[k]) & set(rows)))
+    # pack components into 6-row segments (first-fit in order of their first pivot column)
+    segments = []
+    for rows in comps:
+        for seg in segments:
+            if len(seg) + len(rows) <= 6 and len(seg) < 6 and len(rows) < 6:
+                seg.extend(rows)
+                break
+        else:
+            segments.append(list(rows))
+    segments = [sorted(seg) for seg in segments]
+    assert all(len(seg) <= 6 for seg in segments) and len(segments) * 6 <= WARP and sum(len(x) for x in segments) == N
+    seg_cols = []
+    for seg in segments:
+        cols = [k for k in range(K1) if set(cand_of[k]) <= set(seg) and cand_of[k]]
+        seg_cols.append(cols)
+    assert sorted(c for cols in seg_cols for c in cols) == list(range(K1))
+    # every structurally possible non-zero of a row lies in its segment's private columns or in the dense columns
+    for g, seg in enumerate(segments):
+        for r in seg:
+            for c in range(K1):
+                assert (not P[r, c]) or c in seg_cols[g], (r, c)
+    return K1, segments, seg_cols
+
+
 def build():
     hx, ht = load_tables()
     hx_terms, h_terms = parse_terms(hx, ht)
@@ -114,6 +180,21 @@ def build():
     dq_list = [(0, P_PAD, P_PAD)] + sorted(dq_keys, key=lambda k: (k[2] == P_PAD, k[1], k[2], k[0]))
     dq_index = {k: i for i, k in enumerate(dq_list)}
 
+    # ---- block structure -> lane permutation and register slots -------------------------------------------
+    K1, segments, seg_cols = analyze_blocks(hx_terms)
+    SEG = 6
+    row_of_lane = [-1] * WARP
+    for g, seg in enumerate(segments):
+        for i, r in enumerate(seg):
+            row_of_lane[g * SEG + i] = r
+    lane_of_row = [row_of_lane.index(r) for r in range(N)]
+    nsp = max(len(c) for c in seg_cols)
+    nd = N - K1
+
+    def slot_of(lane, col):
+        g = lane // SEG
+        return seg_cols[g].index(col) if col < K1 else nsp + (col - K1)
+
     # ---- Hx: classes + slots ------------------------------------------------------------------------------
     classes = column_classes(hx_terms)
     col_class = {c: ci for ci, cl in enumerate(classes) for c in cl}
@@ -122,11 +203,12 @@ def build():
         seqs = []
         for lane in range(WARP):
             seq = []
-            if lane < N:
-                cols = [c for c in cl if (lane, c) in hx_terms]
+            row = row_of_lane[lane]
+            if row >= 0:
+                cols = [c for c in cl if (row, c) in hx_terms]
                 assert len(cols) <= 1
                 if cols:
-                    for c, a, b, xs in hx_terms[(lane, cols[0])]:
+                    for c, a, b, xs in hx_terms[(row, cols[0])]:
                         seq.append((cq_index[(c, a, b)], xs))
             seqs.append(seq)
         for row in schedule(seqs):
@@ -136,8 +218,8 @@ def build():
         seqs = []
         for lane in range(WARP):
             seq = []
-            if lane < N:
-                for c, a, b, xs in terms_of_row[lane]:
+            if row_of_lane[lane] >= 0:
+                for c, a, b, xs in terms_of_row[row_of_lane[lane]]:
                     if drop_const and a == P_PAD and b == P_PAD:
                         continue      # d/dt of a parameter-free term vanishes (…L2Cache.cuh:107-118 adds an exact 0)
                     seq.append((index[(c, a, b)], xs))
@@ -146,8 +228,42 @@ def build():
 
     h_slots = sched_rows(h_terms, cq_index, False)
     ht_slots = sched_rows(h_terms, dq_index, True)
+
+    # ---- scatter of the class accumulators into register slots --------------------------------------------------
+    # slot t of a lane holds column seg_cols[g][t] (t < nsp) or K1 + (t - nsp); the class feeding it may depend on the
+    # segment -> at most two candidates per slot, chosen by one per-lane selector bit
+    nslot = nsp + nd
+    scatter = []           # per slot: (classA, classB or -1, selector bit index or -1)
+    sel_of_lane = [0] * WARP
+    nz_of_lane = [0] * WARP
+    n_sel = 0
+    for t in range(nslot):
+        cls_per_seg = []
+        for g in range(len(segments)):
+            col = (seg_cols[g][t] if t < len(seg_cols[g]) else None) if t < nsp else K1 + (t - nsp)
+            cls_per_seg.append(col_class.get(col) if col is not None else None)
+        used = sorted({c for c in cls_per_seg if c is not None})
+        assert 1 <= len(used) <= 2
+        if len(used) == 1:
+            scatter.append((used[0], -1, -1))
+        else:
+            scatter.append((used[0], used[1], n_sel))
+            for lane in range(WARP):
+                g = lane // SEG
+                if g < len(segments) and cls_per_seg[g] == used[1]:
+                    sel_of_lane[lane] |= 1 << n_sel
+            n_sel += 1
+    for lane in range(WARP):
+        row = row_of_lane[lane]
+        if row < 0:
+            continue
+        for c in range(N):
+            if (row, c) in hx_terms:
+                nz_of_lane[lane] |= 1 << slot_of(lane, c)
     return dict(hx_terms=hx_terms, h_terms=h_terms, cq_list=cq_list, dq_list=dq_list, classes=classes,
-                col_class=col_class, hx_slots=hx_slots, h_slots=h_slots, ht_slots=ht_slots)
+                col_class=col_class, hx_slots=hx_slots, h_slots=h_slots, ht_slots=ht_slots,
+                K1=K1, segments=segments, seg_cols=seg_cols, row_of_lane=row_of_lane, lane_of_row=lane_of_row,
+                nsp=nsp, nd=nd, nslot=nslot, scatter=scatter, sel_of_lane=sel_of_lane, nz_of_lane=nz_of_lane, n_sel=n_sel)
 
 
 def pack_word(payload):
@@ -220,24 +336,40 @@ def emit(g, path):
     for r in rows:
         w("  " + ",".join("0x%08xu" % v for v in r) + ", \\")
     w("}")
-    # per-lane bitmask of structurally non-zero columns (row = lane)
-    masks = []
+    # ---- block structure ----------------------------------------------------------------------------------------
+    w("// block structure: %d segments of 6 lanes; sparse pivot columns per segment %s; dense columns %d..%d"
+      % (len(g["segments"]), g["seg_cols"], g["K1"], N - 1))
+    w("#define HCG_K1 %d        /* first dense pivot column */" % g["K1"])
+    w("#define HCG_NSP %d        /* sparse slots (super-steps) */" % g["nsp"])
+    w("#define HCG_ND %d        /* dense slots */" % g["nd"])
+    w("#define HCG_NSLOT %d     /* register slots per row */" % g["nslot"])
+    w("#define HCG_SEG 6")
+    w("#define HCG_NSEG %d" % len(g["segments"]))
+    w("#define HCG_ROW_OF_LANE_INIT { " + ",".join(str(r) for r in g["row_of_lane"]) + " }")
+    w("#define HCG_LANE_OF_ROW_INIT { " + ",".join(str(r) for r in g["lane_of_row"]) + " }")
+    # per-lane info word: nz mask over slots (bits 0..nslot-1) | selector bits << 20 | number of sparse columns << 24
+    info, cols = [], []
     for lane in range(WARP):
-        m = 0
-        for c in range(N):
-            if (lane, c) in g["hx_terms"]:
-                m |= 1 << c
-        masks.append(m)
-    w("#define HCG_NZMASK_INIT { " + ",".join("0x%08xu" % m for m in masks) + " }")
+        gseg = lane // 6
+        ns = len(g["seg_cols"][gseg]) if gseg < len(g["segments"]) and g["row_of_lane"][lane] >= 0 else 0
+        assert g["nslot"] <= 20 and g["n_sel"] <= 4
+        info.append(g["nz_of_lane"][lane] | (g["sel_of_lane"][lane] << 20) | (ns << 24))
+        packed = 0
+        if ns:
+            for t, c in enumerate(g["seg_cols"][gseg]):
+                packed |= c << (5 * t)
+        cols.append(packed)
+    w("#define HCG_LANEINFO_INIT { " + ",".join("0x%08xu" % v for v in info) + " }")
+    w("#define HCG_LANECOLS_INIT { " + ",".join("0x%08xu" % v for v in cols) + " }   /* 5 bits per sparse slot: its matrix column */")
     w("// X(slot, class): one Hx term slot; acc[class] += cq * x_d * x_e")
     w("#define HCG_HX_SLOT_LIST(X) \\")
     for s, (ci, _) in enumerate(g["hx_slots"]):
         w("  X(%d, %d) \\" % (s, ci))
     w("")
-    w("// X(col, class): rA[col] = lane has a non-zero in col ? acc[class] : 0")
+    w("// X(slot, classA, classB, selbit): A[slot] = lane has a non-zero there ? acc[selbit set ? classB : classA] : 0")
     w("#define HCG_HX_SCATTER_LIST(X) \\")
-    for c in range(N):
-        w("  X(%d, %d) \\" % (c, g["col_class"].get(c, 0)))
+    for t, (ca, cb, sb) in enumerate(g["scatter"]):
+        w("  X(%d, %d, %d, %d) \\" % (t, ca, cb, sb))
     w("")
 
     w("#endif")
@@ -252,6 +384,9 @@ def main():
     out = os.path.join(PKG, "csrc", "hc_problem_gen.h")
     emit(g, out)
     print("classes:", g["classes"])
+    print("K1 %d segments %s seg_cols %s" % (g["K1"], g["segments"], g["seg_cols"]))
+    print("row_of_lane", g["row_of_lane"])
+    print("scatter", g["scatter"])
     print("cq entries %d, dq entries %d" % (len(g["cq_list"]), len(g["dq_list"])))
     print("Hx slots %d (ref 240), H slots %d (ref 16), Ht slots %d (ref 16)" %
           (len(g["hx_slots"]), len(g["h_slots"]), len(g["ht_slots"])))
