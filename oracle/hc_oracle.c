@@ -45,8 +45,12 @@ static inline uint32_t f_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u
 static inline uint32_t key_bits(float f) { return (f != f) ? 0x7fffffffu : f_bits(f); }
 
 /* ------------------------------------------------------------------------------------------------------------
- * evaluators — literal restatement of cpu-eval-indx_trifocal_2op1p_30x30.hpp:22-89: every factor position is
- * multiplied, padded ones (p[33] == 1, x[30] == 1) included, left to right, terms added in table order.
+ * evaluators — restatement of cpu-eval-indx_trifocal_2op1p_30x30.hpp:22-89: every entry is the sum, in table order, of
+ *     coef * p[a] * p[b] * x[d] * x[e] (* x[f])
+ * The reference multiplies left to right; the spec groups each term as  (coef * p[a]*p[b]) * (x[d]*x[e]*x[f])  — the
+ * parameter part and the variable part are formed separately (each left to right) and multiplied once, so that an
+ * implementation can share both parts between rows.  Padded factors: p[33] == 1 is multiplied like any parameter (p is
+ * always finite, so that is exact); trailing padded x factors (index 30) are skipped, an all-padded variable part is 1.
  * Table index: Hx (col*40 + term*5 + part)*30 + row ; Ht/H (term*6 + part)*30 + row  (SURVEY.md App. A.3). */
 void hco_param_homotopy(float t, const hco_c32* start34, const hco_c32* target34, hco_c32* p34)
 {
@@ -62,6 +66,15 @@ void hco_param_homotopy(float t, const hco_c32* start34, const hco_c32* target34
 static inline hco_c32 coef_pp(int coef, hco_c32 pa, hco_c32 pb)   /* coef * p[a] * p[b] */
 { return c_scale((float)coef, c_mul(pa, pb)); }
 
+static inline hco_c32 x_product(const hco_c32* x, int d, int e, int f)   /* x[d]*x[e]*x[f], padded factors (30) are trailing */
+{
+  if (d == HCO_N) return c_make(1.0f, 0.0f);
+  if (e == HCO_N) return x[d];
+  hco_c32 v = c_mul(x[d], x[e]);
+  if (f == HCO_N) return v;
+  return c_mul(v, x[f]);
+}
+
 void hco_eval_Hx(const int* dHdx, const hco_c32* x, const hco_c32* p, hco_c32* A)
 {
   for (int row = 0; row < HCO_N; row++)
@@ -71,10 +84,9 @@ void hco_eval_Hx(const int* dHdx, const hco_c32* x, const hco_c32* p, hco_c32* A
         const int base = (col * HCO_HX_TERMS * HCO_HX_PARTS + j * HCO_HX_PARTS) * HCO_N + row;
         int coef = dHdx[base];
         if (coef == 0) continue;                               /* adds an exact +0 in the reference */
-        hco_c32 t = coef_pp(coef, p[dHdx[base + 1 * HCO_N]], p[dHdx[base + 2 * HCO_N]]);
-        t = c_mul(t, x[dHdx[base + 3 * HCO_N]]);
-        t = c_mul(t, x[dHdx[base + 4 * HCO_N]]);
-        acc = c_add(acc, t);
+        hco_c32 cq = coef_pp(coef, p[dHdx[base + 1 * HCO_N]], p[dHdx[base + 2 * HCO_N]]);
+        hco_c32 xp = x_product(x, dHdx[base + 3 * HCO_N], dHdx[base + 4 * HCO_N], HCO_N);
+        acc = c_add(acc, c_mul(cq, xp));
       }
       A[row * HCO_N + col] = acc;
     }
@@ -88,11 +100,9 @@ void hco_eval_H(const int* dHdt, const hco_c32* x, const hco_c32* p, hco_c32* b)
       const int base = (j * HCO_HT_PARTS) * HCO_N + row;
       int coef = dHdt[base];
       if (coef == 0) continue;
-      hco_c32 t = coef_pp(coef, p[dHdt[base + 1 * HCO_N]], p[dHdt[base + 2 * HCO_N]]);
-      t = c_mul(t, x[dHdt[base + 3 * HCO_N]]);
-      t = c_mul(t, x[dHdt[base + 4 * HCO_N]]);
-      t = c_mul(t, x[dHdt[base + 5 * HCO_N]]);
-      acc = c_add(acc, t);
+      hco_c32 cq = coef_pp(coef, p[dHdt[base + 1 * HCO_N]], p[dHdt[base + 2 * HCO_N]]);
+      hco_c32 xp = x_product(x, dHdt[base + 3 * HCO_N], dHdt[base + 4 * HCO_N], dHdt[base + 5 * HCO_N]);
+      acc = c_add(acc, c_mul(cq, xp));
     }
     b[row] = acc;
   }
@@ -109,11 +119,9 @@ void hco_eval_Ht(const int* dHdt, const hco_c32* x, const hco_c32* p, const hco_
       if (coef == 0) continue;
       if (ia == HCO_NP && ib == HCO_NP) continue;              /* dp[33] == 0: the term is an exact 0 */
       hco_c32 s = c_add(c_mul(dp[ia], p[ib]), c_mul(dp[ib], p[ia]));
-      hco_c32 t = c_scale((float)coef, s);
-      t = c_mul(t, x[dHdt[base + 3 * HCO_N]]);
-      t = c_mul(t, x[dHdt[base + 4 * HCO_N]]);
-      t = c_mul(t, x[dHdt[base + 5 * HCO_N]]);
-      acc = c_sub(acc, t);                                     /* r_cgesvB -= … (…L2Cache.cuh:110) */
+      hco_c32 dq = c_scale((float)coef, s);
+      hco_c32 xp = x_product(x, dHdt[base + 3 * HCO_N], dHdt[base + 4 * HCO_N], dHdt[base + 5 * HCO_N]);
+      acc = c_sub(acc, c_mul(dq, xp));                         /* r_cgesvB -= … (…L2Cache.cuh:110) */
     }
     b[row] = acc;
   }

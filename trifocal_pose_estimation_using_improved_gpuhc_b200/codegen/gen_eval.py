@@ -16,7 +16,9 @@ What we emit instead (same arithmetic per term, see "evaluation spec" in DESIGN.
     per lane and scattered to the register row afterwards, so Hx needs ~32 term slots per lane instead of 240;
   * every slot multiplies ALL factor positions, padded ones included (x[30] == 1), exactly like the reference's
     `coef * p[a] * p[b] * x[d] * x[e]`; a lane without a term in a slot reads the zero coefficient and x[30];
-  * per-lane operands are one packed 32-bit word per slot:  cq byte offset | x_d<<10 | x_e<<15 | x_f<<20.
+  * x-products: every distinct product x_d*x_e (Hx) or x_d*x_e*x_f (H, Ht) of non-padded factors is computed once per
+    stage by the warp (36 pairs + 84 triples) into shared memory next to x itself, so a term is ONE complex multiply
+    cq * xprod and its per-lane operand word is just two 16-bit byte offsets:  cq offset | xprod offset << 16.
 Term order inside every matrix entry is the table order, so sums are bit-identical to the oracle's
 table-driven evaluation (`oracle/hc_oracle.c`).
 
@@ -195,6 +197,28 @@ def build():
         g = lane // SEG
         return seg_cols[g].index(col) if col < K1 else nsp + (col - K1)
 
+    # ---- x-product table: [x(32 entries, x[30] = 1) | pairs (padded to a multiple of 32) | triples] -------------------
+    pairs, triples = set(), set()
+    for lst in list(hx_terms.values()) + list(h_terms.values()):
+        for c, a, b, xs in lst:
+            if len(xs) == 2:
+                pairs.add(tuple(xs))
+            elif len(xs) == 3:
+                triples.add(tuple(xs))
+    pairs, triples = sorted(pairs), sorted(triples)
+    XP_PAIR0 = 32
+    XP_TRI0 = XP_PAIR0 + ((len(pairs) + WARP - 1) // WARP) * WARP
+    XP_TOTAL = XP_TRI0 + ((len(triples) + 7) // 8) * 8
+
+    def xp_index(xs):
+        if len(xs) == 0:
+            return X_PAD
+        if len(xs) == 1:
+            return xs[0]
+        if len(xs) == 2:
+            return XP_PAIR0 + pairs.index(tuple(xs))
+        return XP_TRI0 + triples.index(tuple(xs))
+
     # ---- Hx: classes + slots ------------------------------------------------------------------------------
     classes = column_classes(hx_terms)
     col_class = {c: ci for ci, cl in enumerate(classes) for c in cl}
@@ -209,7 +233,7 @@ def build():
                 assert len(cols) <= 1
                 if cols:
                     for c, a, b, xs in hx_terms[(row, cols[0])]:
-                        seq.append((cq_index[(c, a, b)], xs))
+                        seq.append((cq_index[(c, a, b)], xp_index(xs)))
             seqs.append(seq)
         for row in schedule(seqs):
             hx_slots.append((ci, row))
@@ -222,7 +246,7 @@ def build():
                 for c, a, b, xs in terms_of_row[row_of_lane[lane]]:
                     if drop_const and a == P_PAD and b == P_PAD:
                         continue      # d/dt of a parameter-free term vanishes (…L2Cache.cuh:107-118 adds an exact 0)
-                    seq.append((index[(c, a, b)], xs))
+                    seq.append((index[(c, a, b)], xp_index(xs)))
             seqs.append(seq)
         return schedule(seqs)
 
@@ -263,17 +287,20 @@ def build():
     return dict(hx_terms=hx_terms, h_terms=h_terms, cq_list=cq_list, dq_list=dq_list, classes=classes,
                 col_class=col_class, hx_slots=hx_slots, h_slots=h_slots, ht_slots=ht_slots,
                 K1=K1, segments=segments, seg_cols=seg_cols, row_of_lane=row_of_lane, lane_of_row=lane_of_row,
-                nsp=nsp, nd=nd, nslot=nslot, scatter=scatter, sel_of_lane=sel_of_lane, nz_of_lane=nz_of_lane, n_sel=n_sel)
+                nsp=nsp, nd=nd, nslot=nslot, scatter=scatter, sel_of_lane=sel_of_lane, nz_of_lane=nz_of_lane, n_sel=n_sel,
+                pairs=pairs, triples=triples, XP_PAIR0=XP_PAIR0, XP_TRI0=XP_TRI0, XP_TOTAL=XP_TOTAL)
 
 
 def pack_word(payload):
-    if payload is None:
-        idx, xs = 0, []
-    else:
-        idx, xs = payload
+    """cq byte offset (16 bits) | x-product byte offset << 16; an empty slot reads cq[0] == 0 and x[30] == 1."""
+    idx, xp = (0, X_PAD) if payload is None else payload
+    return (idx * 8) | ((xp * 8) << 16)
+
+
+def pack_xp_word(xs):
+    """x byte offsets of up to three factors, 8 bits each (x[i] is entry i of the x-product array)."""
     xs = list(xs) + [X_PAD] * (3 - len(xs))
-    assert idx * 8 < 1024
-    return (idx * 8) | (xs[0] << 10) | (xs[1] << 15) | (xs[2] << 20)
+    return (xs[0] * 8) | ((xs[1] * 8) << 8) | ((xs[2] * 8) << 16)
 
 
 def pack_build_word(key):
@@ -306,10 +333,21 @@ def emit(g, path):
     w("#define HCG_HX_NNZ %d" % nnz)
     w("#define HCG_HX_TERMS %d" % nterms)
     w("#define HCG_H_TERMS %d" % sum(len(v) for v in g["h_terms"].values()))
-    # word table layout: [cq build rounds][dq build rounds][hx slots][h slots][ht slots], 32 words each
+    # word table layout: [cq build rounds][dq build rounds][pair rounds][triple rounds][hx slots][h slots][ht slots], 32 words each
     off_cq = 0
     off_dq = off_cq + rounds(ncq)
-    off_hx = off_dq + rounds(ndq)
+    off_pair = off_dq + rounds(ndq)
+    off_tri = off_pair + rounds(len(g["pairs"]))
+    off_hx = off_tri + rounds(len(g["triples"]))
+    w("#define HCG_XP_PAIR0 %d   /* x-product array: [0,32) x itself, then %d pairs, then %d triples */" % (g["XP_PAIR0"], len(g["pairs"]), len(g["triples"])))
+    w("#define HCG_XP_TRI0 %d" % g["XP_TRI0"])
+    w("#define HCG_XP_TOTAL %d" % g["XP_TOTAL"])
+    w("#define HCG_NUM_PAIRS %d" % len(g["pairs"]))
+    w("#define HCG_NUM_TRIPLES %d" % len(g["triples"]))
+    w("#define HCG_PAIR_ROUNDS %d" % rounds(len(g["pairs"])))
+    w("#define HCG_TRI_ROUNDS %d" % rounds(len(g["triples"])))
+    w("#define HCG_TBL_PAIR %d" % off_pair)
+    w("#define HCG_TBL_TRI %d" % off_tri)
     off_h = off_hx + len(g["hx_slots"])
     off_ht = off_h + len(g["h_slots"])
     total = off_ht + len(g["ht_slots"])
@@ -324,6 +362,9 @@ def emit(g, path):
         for r in range(rounds(n)):
             rows.append([pack_build_word(lst[r * WARP + l]) if r * WARP + l < n else pack_build_word((0, P_PAD, P_PAD))
                          for l in range(WARP)])
+    for lst in (g["pairs"], g["triples"]):
+        for r in range(rounds(len(lst))):
+            rows.append([pack_xp_word(lst[r * WARP + l]) if r * WARP + l < len(lst) else pack_xp_word([]) for l in range(WARP)])
     for _, row in g["hx_slots"]:
         rows.append([pack_word(p) for p in row])
     for row in g["h_slots"]:
@@ -361,7 +402,7 @@ def emit(g, path):
         cols.append(packed)
     w("#define HCG_LANEINFO_INIT { " + ",".join("0x%08xu" % v for v in info) + " }")
     w("#define HCG_LANECOLS_INIT { " + ",".join("0x%08xu" % v for v in cols) + " }   /* 5 bits per sparse slot: its matrix column */")
-    w("// X(slot, class): one Hx term slot; acc[class] += cq * x_d * x_e")
+    w("// X(slot, class): one Hx term slot; acc[class] += cq * xprod")
     w("#define HCG_HX_SLOT_LIST(X) \\")
     for s, (ci, _) in enumerate(g["hx_slots"]):
         w("  X(%d, %d) \\" % (s, ci))
