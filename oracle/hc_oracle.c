@@ -31,12 +31,13 @@ static inline hco_c32 c_msub(hco_c32 acc, hco_c32 m, hco_c32 u)
   return c_make(re, im);
 }
 /* 1/z = conj(z) / |z|^2 with ONE IEEE reciprocal.  The reference divides with cuCdivf (MAGMA_C_DIV,
- * dev-cgesv-batched-small.cuh:84), which pre-scales by |re|+|im| to survive |z| outside [1e-19, 1e19]; pivots of this
- * system never leave that range unless the matrix is numerically singular, and the unscaled form saves a reciprocal
- * per elimination step on the device. */
+ * dev-cgesv-batched-small.cuh:84), which pre-scales by |re|+|im|; here |z|^2 is clamped to [2^-100, 2^100] instead
+ * (|pivot| in [9e-16, 1e15] — a pivot outside that range means a numerically singular or overflowed system), which keeps the
+ * reciprocal's argument in the range where the device's MUFU.RCP + one FMA-Newton step is the correctly rounded 1/d. */
 static inline hco_c32 c_recip(hco_c32 z)
 {
   float d = fmaf(z.re, z.re, z.im * z.im);
+  d = fminf(fmaxf(d, 0x1p-100f), 0x1p100f);
   float q = 1.0f / d;
   return c_make(z.re * q, -(z.im * q));
 }
@@ -134,8 +135,9 @@ void hco_eval_Ht(const int* dHdt, const hco_c32* x, const hco_c32* p, const hco_
  * Gauss-Jordan: rows that were already pivoted are swept too, which performs the U-solve (:97-106) inside the same 30
  * steps; x_k = b_pivot(k) * (1/pivot_k).  Three rules make the result independent of HOW a (block-parallel) implementation
  * schedules the steps:
- *   - ties of the pivot key are broken by the lowest ROW index (the reference takes the first maximum in its current,
- *     virtually permuted row order, :57-65 — same set of maxima, different member in the rare exact-tie case);
+ *   - the pivot is the row with the largest key after the key's five lowest mantissa bits are replaced by (31 - row index):
+ *     i.e. the largest |re|+|im| to within 2^-18 relative, lowest row index among (near-)ties — one integer maximum finds
+ *     the row.  (The reference takes the first exact maximum in its current, virtually permuted row order, :57-65.);
  *   - a row whose entry in the pivot column is exactly zero is not touched (its multiplier would be 0);
  *   - a pivot column whose candidates are all exactly zero makes the system singular: every component of the result is NaN
  *     (the reference continues with a multiplier of 1 and later divides by the zero diagonal, :66-68,100). */
@@ -145,19 +147,17 @@ int hco_solve(hco_c32* A, hco_c32* b)
   hco_c32 rsave[HCO_N];
   for (int i = 0; i < HCO_N; i++) done[i] = 0;
   for (int k = 0; k < HCO_N; k++) {
-    uint32_t maxbits = 0;
-    uint32_t key[HCO_N];
+    uint32_t maxkey = 0;
+    int p = -1;
     for (int i = 0; i < HCO_N; i++) {
-      key[i] = done[i] ? 0u : key_bits(fabsf(A[i * HCO_N + k].re) + fabsf(A[i * HCO_N + k].im));
-      if (key[i] > maxbits) maxbits = key[i];
+      if (done[i]) continue;
+      const uint32_t key = (key_bits(fabsf(A[i * HCO_N + k].re) + fabsf(A[i * HCO_N + k].im)) & ~31u) | (uint32_t)(31 - i);
+      if (key > maxkey) { maxkey = key; p = i; }
     }
-    if (maxbits == 0) {
+    if (maxkey < 32u) {                                  /* every candidate is (within 2^-144 of) zero */
       for (int i = 0; i < HCO_N; i++) b[i] = c_make(NAN, NAN);
       return k + 1;
     }
-    int p = -1;
-    for (int i = 0; i < HCO_N && p < 0; i++)
-      if (!done[i] && key[i] == maxbits) p = i;
     done[p] = 1; piv[k] = p;
     const hco_c32 r = c_recip(A[p * HCO_N + k]);
     rsave[p] = r;
