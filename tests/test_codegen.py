@@ -26,42 +26,78 @@ def test_table_statistics_match_survey():
 
 
 def _unpack(word):
-    return word & 0x3ff, [(word >> 10) & 31, (word >> 15) & 31, (word >> 20) & 31]
+    return word & 0xffff, word >> 16
+
+
+def _xs_of(g, xp_off):
+    """invert the x-product offset: entry of x itself, of the pair table, or of the triple table"""
+    i = xp_off // 8
+    if i < 32:
+        return [] if i == 30 else [i]
+    if i < g["XP_TRI0"]:
+        return list(g["pairs"][i - g["XP_PAIR0"]])
+    return list(g["triples"][i - g["XP_TRI0"]])
 
 
 def test_schedule_covers_every_term_once_in_table_order():
     g = gen_eval.build()
-    # Hx: per (row, class) the slot sequence must equal the row's entry in that class
+    rol = g["row_of_lane"]
+    assert sorted(r for r in rol if r >= 0) == list(range(30)) and rol[30] == rol[31] == -1
+    # Hx: per (lane, class) the slot sequence must equal the entry of the lane's ROW in that class
     for lane in range(30):
+        row = rol[lane]
         for ci, cols in enumerate(g["classes"]):
-            mine = [c for c in cols if (lane, c) in g["hx_terms"]]
+            mine = [c for c in cols if (row, c) in g["hx_terms"]]
             assert len(mine) <= 1
-            want = g["hx_terms"][(lane, mine[0])] if mine else []
+            want = g["hx_terms"][(row, mine[0])] if mine else []
             got = []
-            for cls, row in g["hx_slots"]:
+            for cls, slot_row in g["hx_slots"]:
                 if cls != ci:
                     continue
-                off, xs = _unpack(gen_eval.pack_word(row[lane]))
+                off, xp = _unpack(gen_eval.pack_word(slot_row[lane]))
                 if off == 0:
-                    assert xs == [30, 30, 30]
+                    assert xp == 30 * 8          # empty slot: zero coefficient times x[30] == 1
                     continue
                 c, a, b = g["cq_list"][off // 8]
-                got.append((c, a, b, [x for x in xs[:2] if x != 30]))
+                got.append((c, a, b, _xs_of(g, xp)))
             assert got == want
     for name, lst, drop in (("h_slots", g["cq_list"], False), ("ht_slots", g["dq_list"], True)):
         for lane in range(30):
-            want = [(c, a, b, xs) for (c, a, b, xs) in g["h_terms"][lane] if not (drop and a == 33 and b == 33)]
+            want = [(c, a, b, xs) for (c, a, b, xs) in g["h_terms"][rol[lane]] if not (drop and a == 33 and b == 33)]
             got = []
-            for row in g[name]:
-                off, xs = _unpack(gen_eval.pack_word(row[lane]))
+            for slot_row in g[name]:
+                off, xp = _unpack(gen_eval.pack_word(slot_row[lane]))
                 if off == 0:
                     continue
                 c, a, b = lst[off // 8]
-                got.append((c, a, b, [x for x in xs if x != 30]))
+                got.append((c, a, b, _xs_of(g, xp)))
             assert got == want
     # lanes 30, 31 never hold a term
-    for _, row in g["hx_slots"]:
-        assert row[30] is None and row[31] is None
+    for _, slot_row in g["hx_slots"]:
+        assert slot_row[30] is None and slot_row[31] is None
+
+
+def test_block_structure_is_what_the_kernel_assumes():
+    """analyze_blocks: 18 sparse pivot columns in five independent 6-row groups, 12 shared columns, 17 register slots."""
+    g = gen_eval.build()
+    assert g["K1"] == 18 and g["nsp"] == 5 and g["nd"] == 12 and g["nslot"] == 17
+    assert g["segments"] == [[3, 4, 5, 12, 13, 14], [6, 7, 8, 15, 16, 17], [0, 1, 2, 9, 10, 11], [18, 19, 20, 24, 25, 26], [21, 22, 23, 27, 28, 29]]
+    assert g["seg_cols"] == [[0, 3, 6], [1, 4, 7], [2, 5], [8, 9, 12, 13, 14], [10, 11, 15, 16, 17]]
+    # every structural non-zero of a row is in one of the row's slots, and rows are ascending inside a segment
+    for lane, row in enumerate(g["row_of_lane"]):
+        if row < 0:
+            continue
+        seg = lane // 6
+        for c in range(30):
+            if (row, c) in g["hx_terms"]:
+                assert c >= g["K1"] or c in g["seg_cols"][seg]
+    for seg in g["segments"]:
+        assert seg == sorted(seg)
+    # independence that makes the block-parallel schedule exact: a sparse column is non-zero only inside its own segment
+    for (row, c) in g["hx_terms"]:
+        if c < g["K1"]:
+            owner = [i for i, cols in enumerate(g["seg_cols"]) if c in cols][0]
+            assert row in g["segments"][owner]
 
 
 def test_column_classes_partition_the_nonzero_columns():
