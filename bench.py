@@ -196,7 +196,8 @@ def main():
     ap.add_argument("--hyp", type=int, default=100, help="hypotheses per GPU per step (100 = default RANSAC round)")
     ap.add_argument("--abort", action="store_true", help="Abort_RANSAC_by_Good_Sol = true (configs[2])")
     ap.add_argument("--no-prune", action="store_true")
-    ap.add_argument("--ref-hyp", type=int, default=8, help="hypotheses per step of the reference CPU arm / cpu_baseline sample")
+    ap.add_argument("--ref-hyp", type=int, default=8, help="hypotheses per step of the reference CPU arm (--impl reference)")
+    ap.add_argument("--cpu-baseline-hyp", type=int, default=40, help="hypotheses of the cpu_baseline sample (about 15 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference GPU-HC++ kernels (oracle/_ref/libref_gpuhc.so)")
     args = ap.parse_args()
@@ -353,7 +354,7 @@ def main():
                 rg["speedup_ours_vs_ref_gpu"] = rg["ms_per_step"] / ms_per_step
                 line["ref_gpu"] = rg
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline_leg(args.ref_hyp)
+            line["cpu_baseline"] = cpu_baseline_leg(args.cpu_baseline_hyp)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

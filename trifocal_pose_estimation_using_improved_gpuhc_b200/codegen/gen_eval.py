@@ -163,6 +163,60 @@ def analyze_blocks(hx_terms):
     return K1, segments, seg_cols
 
 
+def optimise_layout(n_pos, movable_sets, groups, seed=1):
+    """Table layout against shared-memory bank conflicts.  A 64-bit gather by a half-warp needs as many wavefronts as the
+    largest number of DISTINCT entries that fall into one of the 16 bank pairs (position mod 16).  `groups` lists, for every
+    (term slot, half-warp), the set of table entries gathered together; entries inside one of `movable_sets` may exchange
+    positions.  Deterministic pairwise-swap local search; returns pos[entry]."""
+    import random
+    rnd = random.Random(seed)
+    pos = list(range(n_pos))
+    member = {}
+    for gi, grp in enumerate(groups):
+        for e in grp:
+            member.setdefault(e, []).append(gi)
+
+    def gcost(gi):
+        cnt = {}
+        for e in groups[gi]:
+            k = pos[e] % 16
+            cnt[k] = cnt.get(k, 0) + 1
+        return max(cnt.values())
+
+    cost = [gcost(gi) for gi in range(len(groups))]
+    for mv in movable_sets:
+        mv = list(mv)
+        for sweep in range(8):
+            improved = False
+            rnd.shuffle(mv)
+            for i in range(len(mv)):
+                for j in range(i + 1, len(mv)):
+                    e, f = mv[i], mv[j]
+                    affected = set(member.get(e, [])) | set(member.get(f, []))
+                    if not affected:
+                        continue
+                    before = sum(cost[gi] for gi in affected)
+                    pos[e], pos[f] = pos[f], pos[e]
+                    after = {gi: gcost(gi) for gi in affected}
+                    if sum(after.values()) < before:
+                        for gi, c in after.items():
+                            cost[gi] = c
+                        improved = True
+                    else:
+                        pos[e], pos[f] = pos[f], pos[e]
+            if not improved:
+                break
+    return pos, sum(cost)
+
+
+def _groups(slot_rows, field, pad_entry):
+    out = []
+    for row in slot_rows:
+        for half in (range(0, 16), range(16, 32)):
+            out.append({pad_entry if row[l] is None else row[l][field] for l in half})
+    return out
+
+
 def build():
     hx, ht = load_tables()
     hx_terms, h_terms = parse_terms(hx, ht)
@@ -253,6 +307,37 @@ def build():
     h_slots = sched_rows(h_terms, cq_index, False)
     ht_slots = sched_rows(h_terms, dq_index, True)
 
+    # ---- bank-conflict-aware table layouts --------------------------------------------------------------------------
+    hx_rows = [row for _, row in hx_slots]
+    cost0 = [sum(max(sum(1 for e in grp if e % 16 == k) for k in range(16)) for grp in _groups(r, f, pe))
+             for r, f, pe in ((hx_rows + h_slots, 0, 0), (ht_slots, 0, 0), (hx_rows + h_slots + ht_slots, 1, X_PAD))]
+    cq_pos, c_cq = optimise_layout(len(cq_list), [range(1, len(cq_list))], _groups(hx_rows + h_slots, 0, 0))
+    dq_pos, c_dq = optimise_layout(len(dq_list), [range(1, len(dq_list))], _groups(ht_slots, 0, 0))
+    xp_pos, c_xp = optimise_layout(XP_TOTAL, [range(XP_PAIR0, XP_TRI0), range(XP_TRI0, XP_TOTAL)],
+                                   _groups(hx_rows + h_slots + ht_slots, 1, X_PAD))
+    layout_cost = dict(before=cost0, after=[c_cq, c_dq, c_xp])
+
+    def remap(rows, cpos):
+        return [[None if p is None else (cpos[p[0]], xp_pos[p[1]]) for p in row] for row in rows]
+
+    hx_slots = [(ci, r) for (ci, _), r in zip(hx_slots, remap(hx_rows, cq_pos))]
+    h_slots = remap(h_slots, cq_pos)
+    ht_slots = remap(ht_slots, dq_pos)
+    # tables in POSITION order (the build rounds walk positions, so their stores stay conflict-free)
+    cq_by_pos = [(0, P_PAD, P_PAD)] * len(cq_list)
+    for e, q in enumerate(cq_pos):
+        cq_by_pos[q] = cq_list[e]
+    dq_by_pos = [(0, P_PAD, P_PAD)] * len(dq_list)
+    for e, q in enumerate(dq_pos):
+        dq_by_pos[q] = dq_list[e]
+    cq_list, dq_list = cq_by_pos, dq_by_pos
+    pair_by_pos = [None] * (XP_TRI0 - XP_PAIR0)
+    for i, pr in enumerate(pairs):
+        pair_by_pos[xp_pos[XP_PAIR0 + i] - XP_PAIR0] = pr
+    tri_by_pos = [None] * (XP_TOTAL - XP_TRI0)
+    for i, tr in enumerate(triples):
+        tri_by_pos[xp_pos[XP_TRI0 + i] - XP_TRI0] = tr
+
     # ---- scatter of the class accumulators into register slots --------------------------------------------------
     # slot t of a lane holds column seg_cols[g][t] (t < nsp) or K1 + (t - nsp); the class feeding it may depend on the
     # segment -> at most two candidates per slot, chosen by one per-lane selector bit
@@ -288,7 +373,8 @@ def build():
                 col_class=col_class, hx_slots=hx_slots, h_slots=h_slots, ht_slots=ht_slots,
                 K1=K1, segments=segments, seg_cols=seg_cols, row_of_lane=row_of_lane, lane_of_row=lane_of_row,
                 nsp=nsp, nd=nd, nslot=nslot, scatter=scatter, sel_of_lane=sel_of_lane, nz_of_lane=nz_of_lane, n_sel=n_sel,
-                pairs=pairs, triples=triples, XP_PAIR0=XP_PAIR0, XP_TRI0=XP_TRI0, XP_TOTAL=XP_TOTAL)
+                pairs=pair_by_pos, triples=tri_by_pos, XP_PAIR0=XP_PAIR0, XP_TRI0=XP_TRI0, XP_TOTAL=XP_TOTAL,
+                layout_cost=layout_cost)
 
 
 def pack_word(payload):
@@ -364,7 +450,8 @@ def emit(g, path):
                          for l in range(WARP)])
     for lst in (g["pairs"], g["triples"]):
         for r in range(rounds(len(lst))):
-            rows.append([pack_xp_word(lst[r * WARP + l]) if r * WARP + l < len(lst) else pack_xp_word([]) for l in range(WARP)])
+            rows.append([pack_xp_word(lst[r * WARP + l]) if r * WARP + l < len(lst) and lst[r * WARP + l] is not None else pack_xp_word([])
+                         for l in range(WARP)])
     for _, row in g["hx_slots"]:
         rows.append([pack_word(p) for p in row])
     for row in g["h_slots"]:
@@ -431,6 +518,7 @@ def main():
     print("cq entries %d, dq entries %d" % (len(g["cq_list"]), len(g["dq_list"])))
     print("Hx slots %d (ref 240), H slots %d (ref 16), Ht slots %d (ref 16)" %
           (len(g["hx_slots"]), len(g["h_slots"]), len(g["ht_slots"])))
+    print("gather wavefront model (cq, dq, xp) before/after layout optimisation:", g["layout_cost"])
     print("hx_slots", [(ci, sum(p is not None for p in row)) for ci, row in g["hx_slots"]])
     print("h_slots", [sum(p is not None for p in row) for row in g["h_slots"]])
     print("ht_slots", [sum(p is not None for p in row) for row in g["ht_slots"]])
