@@ -101,8 +101,10 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": "RANSAC hypotheses/s (312 HC paths each)", "unit": "hypotheses/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "c64", "data": "synthetic",
-            "config": {"workload": "trifocal_2op1p_30x30 default RANSAC round (100 hyp x 312 paths, 80 steps, no abort)",
-                       "hypotheses_per_step": sample, "note": "reference CPU-HC has no path pruning (SURVEY.md App. E-8)"}}
+            "config": {"workload": "trifocal_2op1p_30x30 default RANSAC round: 100 hypotheses x 312 paths per GPU, 80 max steps, "
+                                   "3 corrections, pruning on, early abort off, dataset Synthetic/000, seed 0",
+                       "sample_hypotheses_per_step": sample,
+                       "note": "bounded sample of that round; the reference CPU-HC has no path pruning (SURVEY.md App. E-8)"}}
     try:
         ref = pyoracle.ReferenceCPU()
         kind = "reference"
