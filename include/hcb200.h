@@ -90,6 +90,17 @@ int hcb200_build_target_params(void* stream, int n_hyp, const int32_t* d_picked,
                                const float* d_edgel_locations, const float* d_edgel_tangents,
                                const float* d_start_params, float* d_target_params, float* d_diff_params);
 
+/* Final scoring of a round on the device (Evaluations::Transform_GPUHC_Sols_to_Trifocal_Relative_Pose +
+ * ::get_Solution_with_Maximal_Support, reference Evaluations.cpp:298-504, with the intended per-solution indexing).
+ * For every path: d_support[2*path + {0,1}] = number of edgel triplets whose reprojection error is < 2 px for view pairs
+ * (1,2) / (1,3), or -1 when the path is not a pose candidate (not converged, |Im| of a Cayley parameter >= 1e-5, or a negative
+ * depth).  d_best: found, path_id = candidate maximising min(support21, support31) (lowest path id on ties), its two supports,
+ * n_passed = number of candidates, reserved[0..1] = the per-pair maxima over all candidates.  Uses bytes [128, 160) of the
+ * workspace.  The float arithmetic is the host class's (host/mvg.hpp) operation for operation, so counts are identical. */
+int hcb200_score_tracks(void* stream, int n_paths, const float* d_tracks, const uint8_t* d_converged, int n_edgels,
+                        const float* d_edgel_locations, const float* d_intrinsic, int32_t* d_support,
+                        hcb200_best_record* d_best, void* d_workspace);
+
 /* Introspection for benchmarks/tests: registers per thread, static+dynamic shared bytes per CTA, resident CTAs per SM,
  * grid size a launch would use on the current device.  Any pointer may be NULL. */
 int hcb200_kernel_info(int abort_variant, int* regs, int* smem_bytes, int* ctas_per_sm, int* grid, int* block);

@@ -40,6 +40,7 @@ int    hcb200_solver_per_hypothesis(hcb200_solver* s, unsigned* out /*[H][3] con
 int    hcb200_solver_copy_results(hcb200_solver* s, float* tracks /*[H*312][31][2]*/, uint8_t* conv, uint8_t* inf);
 int    hcb200_solver_copy_target_params(hcb200_solver* s, float* out /*[H][34][2], stacked over GPUs*/);
 int    hcb200_solver_best(hcb200_solver* s, hcb200_best_record* rec, int* pose_found, float residuals_R21_R31_t21_t31[4]);
+int    hcb200_solver_selected(hcb200_solver* s, int* path_id, unsigned support21_31[2]);   /* pose with maximal support; 0 if one exists */
 int    hcb200_solver_shard_size(hcb200_solver* s, int gpu_id);
 
 /* Reference text formats without a device: Data_Reader over <problem_dir> (start_sols.txt, start_params.txt, dHdx_indx.txt,
@@ -50,6 +51,10 @@ int hcb200_reader_load(const char* problem_dir, const char* ransac_dir, int data
                        float* start_sols, float* start_params, int* dHdx, int* dHdt,
                        int* n_edgels, float* locations, float* tangents, int edgel_capacity,
                        float* pose21, float* pose31, float* K);
+/* Host scoring of one end point [31][2] with the arithmetic of Evaluations / mvg.hpp (reference Evaluations.cpp:298-504, util.hpp:169-209):
+ * returns 1 and the two inlier counts if the path is a pose candidate, 0 otherwise.  The device kernel behind
+ * hcb200_score_tracks must agree with it count for count. */
+int hcb200_host_score_track(const float* track31, const float* locations, int n_edgels, const float* K, int* n21, int* n31);
 /* value of one key of a gpuhc_settings.yaml as text; 0 found, 1 missing key, 2 buffer too small, 3 unreadable file */
 int hcb200_settings_lookup(const char* settings_yaml, const char* key, char* out, int capacity);
 

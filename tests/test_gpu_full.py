@@ -139,8 +139,12 @@ class HostSolver:
         res = np.zeros(4, np.float32)
         L.hcb200_solver_best(h, vp(best), ctypes.cast(ctypes.byref(found), ctypes.c_void_p), vp(res))
         sec = L.hcb200_solver_kernel_seconds(h)
+        sel_path = ctypes.c_int()
+        sel_sup = np.zeros(2, np.uint32)
+        L.hcb200_solver_selected.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.hcb200_solver_selected(h, ctypes.cast(ctypes.byref(sel_path), ctypes.c_void_p), vp(sel_sup))
         L.hcb200_solver_free_round(h)
-        return dict(tracks=tr[..., 0] + 1j * tr[..., 1], conv=cv, inf=inf, totals=tot, per=per, best=best, pose_found=found.value,
+        return dict(selected_path=sel_path.value, selected_support=sel_sup.tolist(), tracks=tr[..., 0] + 1j * tr[..., 1], conv=cv, inf=inf, totals=tot, per=per, best=best, pose_found=found.value,
                     residuals=res, seconds=sec, H=H)
 
     def close(self):
@@ -162,6 +166,13 @@ def test_host_class_default_round_matches_golden(tree):
     assert np.array_equal(np.packbits(r["conv"]), g["converged_bits"])
     assert r["pose_found"] == 1 and np.all(r["residuals"] < 0.1) and np.all(r["residuals"][:2] < 1e-2)
     assert 0 < r["seconds"] < 5
+    # pose with maximal support: selected on the device (hcb200_score_tracks); the host-only path must pick the same one
+    assert r["selected_path"] == 104 and r["selected_support"] == [5117, 5117]
+    s2 = HostSolver(tree, "Num_Of_GPUs=1;Device_Scoring=false")
+    r2 = s2.round()
+    s2.close()
+    assert r2["selected_path"] == 104 and r2["selected_support"] == [5117, 5117]
+    assert np.array_equal(r2["residuals"], r["residuals"])
 
 
 def test_host_class_early_abort_finds_gt_pose(tree):
@@ -233,3 +244,38 @@ def test_against_reference_gpu_kernels(problem, ransac0, default_round):
     ref.results()
     idx = ref.d_found_index.cpu().numpy()
     assert bool(ref.d_found.cpu()[0]) and 104 in idx[idx >= 0]
+
+
+def test_device_scoring_matches_host_evaluations(problem, ransac0, default_round):
+    """hcb200_score_tracks vs the host class's arithmetic (hcb200_host_score_track = Evaluations/mvg.hpp): same candidate set,
+    identical inlier counts (integers), same selected pose."""
+    picked, target, diff = default_round
+    H = 40
+    trk = hc.Tracker(problem=problem)
+    trk.set_edgels(ransac0["locations"], ransac0["K"])
+    trk.upload_params(target[:H], diff[:H])
+    trk.track(H, prune=True)
+    tr, cv, inf, _ = trk.results(H)
+    support, best = trk.score_tracks(H)
+    host = ctypes.CDLL(os.path.join(LIBDIR, "libhcb200_host.so"))
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    loc = np.ascontiguousarray(ransac0["locations"], np.float32)
+    K = np.ascontiguousarray(ransac0["K"], np.float32).reshape(-1)
+    n_cand, best_key, best_path = 0, -1, -1
+    for pth in range(H * 312):
+        if not cv[pth]:
+            assert support[pth].tolist() == [-1, -1]
+            continue
+        x = np.ascontiguousarray(np.stack([tr[pth].real, tr[pth].imag], -1).astype(np.float32))
+        n21, n31 = ctypes.c_int(), ctypes.c_int()
+        is_cand = host.hcb200_host_score_track(vp(x), vp(loc), loc.shape[0], vp(K), ctypes.byref(n21), ctypes.byref(n31))
+        if not is_cand:
+            assert support[pth].tolist() == [-1, -1]
+            continue
+        n_cand += 1
+        assert support[pth].tolist() == [n21.value, n31.value], pth
+        if min(n21.value, n31.value) > best_key:
+            best_key, best_path = min(n21.value, n31.value), pth
+    assert n_cand >= 5
+    assert best[0] == 1 and best[1] == best_path == 104 and best[4] == n_cand
+    assert (best[2], best[3]) == (5117, 5117)

@@ -23,7 +23,7 @@ _lib = None
 
 # every symbol include/hcb200.h declares
 ABI_SYMBOLS = ("hcb200_workspace_bytes", "hcb200_abi_version", "hcb200_track", "hcb200_track_abort",
-               "hcb200_build_target_params", "hcb200_kernel_info", "hcb200_ffma_probe", "hcb200_error_string")
+               "hcb200_build_target_params", "hcb200_score_tracks", "hcb200_kernel_info", "hcb200_ffma_probe", "hcb200_error_string")
 
 
 class HCB200Error(RuntimeError):
@@ -53,6 +53,8 @@ def load_library(path=None):
     lib.hcb200_build_target_params.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp]
     lib.hcb200_kernel_info.restype = i32
     lib.hcb200_kernel_info.argtypes = [i32] + [ctypes.POINTER(i32)] * 5
+    lib.hcb200_score_tracks.restype = i32
+    lib.hcb200_score_tracks.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.hcb200_ffma_probe.restype = i32
     lib.hcb200_ffma_probe.argtypes = [vp, i32, vp, ctypes.POINTER(ctypes.c_double)]
     _lib = lib
@@ -229,6 +231,21 @@ class Tracker:
                                              p(self.d_stats), p(self.d_ws))
         _check(rc, "hcb200_track_abort")
         self.launches += 2
+
+    def score_tracks(self, n_hyp):
+        """Device-side final scoring of the last round: returns (support int32 [P,2], best record int32 [16]) after a sync."""
+        torch = self.torch
+        n_paths = n_hyp * NUM_TRACKS
+        if getattr(self, "d_support", None) is None or self.d_support.shape[0] < n_paths:
+            self.d_support = torch.empty((n_paths, 2), dtype=torch.int32, device=self.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            rc = self.lib.hcb200_score_tracks(self._stream(), n_paths, p(self.d_tracks), p(self.d_conv), self.n_edgels, p(self.d_edgels),
+                                              p(self.d_K), p(self.d_support), p(self.d_best), p(self.d_ws))
+        _check(rc, "hcb200_score_tracks")
+        self.launches += 2
+        torch.cuda.synchronize(self.device)
+        return self.d_support[:n_paths].cpu().numpy(), self.d_best.cpu().numpy()
 
     def build_target_params(self, d_picked, d_tangents, n_hyp):
         p = lambda t: ctypes.c_void_p(t.data_ptr())

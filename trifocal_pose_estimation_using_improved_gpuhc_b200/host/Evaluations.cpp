@@ -189,6 +189,16 @@ bool Evaluations::get_Solution_with_Maximal_Support(unsigned n_edgels, float* lo
   return true;
 }
 
+void Evaluations::Set_Selected_Solution(complex32* x, int path_index, unsigned support21, unsigned support31)
+{
+  Convert_Trifocal_Translation(x);
+  Convert_Trifocal_Rotation(x);
+  R21_w_Max_Supports = normalized_R21; t21_w_Max_Supports = normalized_t21;
+  R31_w_Max_Supports = normalized_R31; t31_w_Max_Supports = normalized_t31;
+  Max_Num_Of_Reproj_Inliers_Views21 = support21; Max_Num_Of_Reproj_Inliers_Views31 = support31;
+  Best_Candidate_Path_Index = path_index;
+}
+
 static void split_gt(float GT_Pose[12], mvg::Mat3& R, mvg::Vec3& t)
 {
   for (int i = 0; i < 9; i++) R[i] = GT_Pose[i];                 // rows 0-2 of the 4x3 file = R (row-major), row 3 = t

@@ -32,6 +32,8 @@ public:
   void Measure_Relative_Pose_Error_from_All_Real_Sols(float GT_Pose21[12], float GT_Pose31[12], hcb200::complex32* h_Debug_Purpose);
   void Measure_Relative_Pose_Error(float GT_Pose21[12], float GT_Pose31[12]);
   bool get_Solution_with_Maximal_Support(unsigned Num_Of_Triplet_Edgels, float* h_Triplet_Edge_Locations, float* h_Triplet_Edge_Tangents, float* K);
+  // adopt ONE end point (selected on the device by hcb200_score_tracks) as the pose with maximal support
+  void Set_Selected_Solution(hcb200::complex32* track, int path_index, unsigned support21, unsigned support31);
   void Check_Deviations_of_Veridical_Sol_from_GT(hcb200::complex32* h_GPU_HC_Track_Sols, float GT_Pose21[12], float GT_Pose31[12]);
   void Flush_Out_Data();
   void Write_HC_Steps_of_Actual_Solutions(std::vector<int> steps) { for (int s : steps) HC_Actual_Sols_Steps_File << s << "\n"; }

@@ -47,6 +47,7 @@ GPU_HC_Solver::GPU_HC_Solver(YAML::Node cfg) : Problem_Setting_YAML_File(cfg)
   num_ransac_iters                = cfg.as_or<int>("Num_Of_RANSAC_Iterations", NUM_OF_RANSAC_ITERATIONS);
   const std::string root          = cfg.as_or<std::string>("Repo_Root", "../../");
   verbose                         = cfg.as_or<bool>("Verbose", true);
+  device_scoring                  = cfg.as_or<bool>("Device_Scoring", true);
 
   if (HC_problem != "trifocal_2op1p_30x30" || Num_Of_Vars != HCB200_NUM_VARS || Num_Of_Params != HCB200_NUM_PARAMS ||
       Num_Of_Tracks != HCB200_NUM_TRACKS) {
@@ -121,6 +122,9 @@ void GPU_HC_Solver::Allocate_Arrays()
     HC_CUDA(cudaMalloc((void**)&d.d_conv, paths ? paths : 1));
     HC_CUDA(cudaMalloc((void**)&d.d_inf, paths ? paths : 1));
     HC_CUDA(cudaMalloc(&d.d_ws, hcb200_workspace_bytes()));
+    HC_CUDA(cudaMalloc((void**)&d.d_support, 2 * sizeof(int) * (paths ? paths : 1)));
+    HC_CUDA(cudaMalloc((void**)&d.d_score_best, sizeof(hcb200_best_record)));
+    HC_CUDA(cudaMallocHost((void**)&h_score_best[g], sizeof(hcb200_best_record)));
   }
   arrays_allocated = true;
 }
@@ -188,8 +192,6 @@ void GPU_HC_Solver::Set_RANSAC_Abort_Arrays()
     h_Trifocal_Sols_Batch_Index[g] = new int[paths ? paths : 1];
     for (size_t i = 0; i < paths; i++) h_Trifocal_Sols_Batch_Index[g][i] = -1;
     h_best[g] = new hcb200_best_record();
-    HC_CUDA(cudaMalloc((void**)&d.d_K, 9 * sizeof(float)));
-    HC_CUDA(cudaMalloc((void**)&d.d_edgels, (size_t)Num_Of_Triplet_Edgels * 6 * sizeof(float)));
     HC_CUDA(cudaMalloc((void**)&d.d_found, sizeof(bool)));
     HC_CUDA(cudaMalloc((void**)&d.d_found_index, (paths ? paths : 1) * sizeof(int)));
     HC_CUDA(cudaMalloc((void**)&d.d_best, sizeof(hcb200_best_record)));
@@ -212,9 +214,16 @@ void GPU_HC_Solver::Data_Transfer_From_Host_To_Device()
       HC_CUDA(cudaMemcpyAsync(d.d_target, h_Target_Params[g], sizeof(complex32) * P1 * H, cudaMemcpyHostToDevice, s));
       HC_CUDA(cudaMemcpyAsync(d.d_diff, h_diffParams[g], sizeof(complex32) * P1 * H, cudaMemcpyHostToDevice, s));
     }
-    if (Abort_RANSAC_by_Good_Sol) {
+    if (Abort_RANSAC_by_Good_Sol || device_scoring) {       // the edgel triplets feed the in-kernel abort test and the final scoring
+      if (!d.d_edgels) {
+        HC_CUDA(cudaMalloc((void**)&d.d_K, 9 * sizeof(float)));
+        HC_CUDA(cudaMalloc((void**)&d.d_edgels, (size_t)Num_Of_Triplet_Edgels * 6 * sizeof(float)));
+        device_edgels_allocated = true;
+      }
       HC_CUDA(cudaMemcpyAsync(d.d_edgels, h_Triplet_Edge_Locations, (size_t)Num_Of_Triplet_Edgels * 6 * sizeof(float), cudaMemcpyHostToDevice, s));
       HC_CUDA(cudaMemcpyAsync(d.d_K, h_Camera_Intrinsic_Matrix, 9 * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    if (Abort_RANSAC_by_Good_Sol) {
       if (paths) HC_CUDA(cudaMemcpyAsync(d.d_found_index, h_Trifocal_Sols_Batch_Index[g], paths * sizeof(int), cudaMemcpyHostToDevice, s));
       HC_CUDA(cudaMemcpyAsync(d.d_found, h_Found_Trifocal_Sols[g], sizeof(bool), cudaMemcpyHostToDevice, s));
     }
@@ -315,16 +324,55 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
   Collect_Num_Of_Inf_Sols.push_back(Evaluate_GPUHC_Sols->Num_Of_Inf_Sols);
   Collect_Num_Of_Real_Sols.push_back(Evaluate_GPUHC_Sols->Num_Of_Real_Sols);
 
-  Evaluate_GPUHC_Sols->Transform_GPUHC_Sols_to_Trifocal_Relative_Pose(h_GPU_HC_Track_Sols_Stack, h_is_GPU_HC_Sol_Converge_Stack, h_Camera_Intrinsic_Matrix);
-  found_pose = Evaluate_GPUHC_Sols->get_Solution_with_Maximal_Support(Num_Of_Triplet_Edgels, h_Triplet_Edge_Locations, h_Triplet_Edge_Tangents, h_Camera_Intrinsic_Matrix);
+  selected_path = -1;
+  selected_support = {0u, 0u};
+  if (device_scoring) {
+    // support counting + selection on every GPU (hcb200_score_tracks), then the tiny gather: one 64-byte record per GPU,
+    // reduced on the host — largest min(support21, support31), lowest global path id on ties
+    for (int g = 0; g < Num_Of_GPUs; g++) {
+      DeviceShard& d = shard[g];
+      const int paths = sub_RANSAC_iters[g] * Num_Of_Tracks;
+      if (!paths) continue;
+      HC_CUDA(cudaSetDevice(d.device));
+      const int rc = hcb200_score_tracks(d.stream, paths, d.d_tracks, d.d_conv, Num_Of_Triplet_Edgels, d.d_edgels, d.d_K, d.d_support,
+                                         d.d_score_best, d.d_ws);
+      if (rc != 0) { std::fprintf(stderr, "[ERROR] scoring launch failed on GPU %d: %s\n", g, hcb200_error_string(rc)); std::exit(2); }
+      HC_CUDA(cudaMemcpyAsync(h_score_best[g], d.d_score_best, sizeof(hcb200_best_record), cudaMemcpyDeviceToHost, (cudaStream_t)d.stream));
+    }
+    unsigned best_min = 0;
+    for (int g = 0; g < Num_Of_GPUs; g++) {
+      if (!sub_RANSAC_iters[g]) continue;
+      HC_CUDA(cudaSetDevice(shard[g].device));
+      HC_CUDA(cudaStreamSynchronize((cudaStream_t)shard[g].stream));
+      const hcb200_best_record& r = *h_score_best[g];
+      if (!r.found) continue;
+      const unsigned m = (unsigned)std::min(r.inliers21, r.inliers31);
+      if (selected_path < 0 || m > best_min) {
+        best_min = m;
+        selected_path = shard[g].path_offset + r.path_id;
+        selected_support = {(unsigned)r.inliers21, (unsigned)r.inliers31};
+      }
+    }
+    found_pose = selected_path >= 0;
+    if (found_pose)
+      Evaluate_GPUHC_Sols->Set_Selected_Solution(h_GPU_HC_Track_Sols_Stack + (size_t)selected_path * V1, selected_path,
+                                                 selected_support[0], selected_support[1]);
+  } else {
+    Evaluate_GPUHC_Sols->Transform_GPUHC_Sols_to_Trifocal_Relative_Pose(h_GPU_HC_Track_Sols_Stack, h_is_GPU_HC_Sol_Converge_Stack, h_Camera_Intrinsic_Matrix);
+    found_pose = Evaluate_GPUHC_Sols->get_Solution_with_Maximal_Support(Num_Of_Triplet_Edgels, h_Triplet_Edge_Locations, h_Triplet_Edge_Tangents, h_Camera_Intrinsic_Matrix);
+    if (found_pose) {
+      selected_path = Evaluate_GPUHC_Sols->Best_Candidate_Path_Index;
+      selected_support = {Evaluate_GPUHC_Sols->Max_Num_Of_Reproj_Inliers_Views21, Evaluate_GPUHC_Sols->Max_Num_Of_Reproj_Inliers_Views31};
+    }
+  }
   pose_residuals = {100.f, 100.f, 100.f, 100.f};
   if (found_pose) {
     Evaluate_GPUHC_Sols->Measure_Relative_Pose_Error(h_Camera_Pose21, h_Camera_Pose31);
     pose_residuals = {Evaluate_GPUHC_Sols->Min_Residual_R21, Evaluate_GPUHC_Sols->Min_Residual_R31,
                       Evaluate_GPUHC_Sols->Min_Residual_t21, Evaluate_GPUHC_Sols->Min_Residual_t31};
     if (verbose) {
-      std::printf("## Pose with maximal support: path %d, inliers (1,2) %u / (1,3) %u of %d\n", Evaluate_GPUHC_Sols->Best_Candidate_Path_Index,
-                  Evaluate_GPUHC_Sols->Max_Num_Of_Reproj_Inliers_Views21, Evaluate_GPUHC_Sols->Max_Num_Of_Reproj_Inliers_Views31, Num_Of_Triplet_Edgels);
+      std::printf("## Pose with maximal support: path %d, inliers (1,2) %u / (1,3) %u of %d\n", selected_path,
+                  selected_support[0], selected_support[1], Num_Of_Triplet_Edgels);
       std::printf(" - residuals vs GT: R21 %.3g rad, R31 %.3g rad, t21 %.3g, t31 %.3g%s\n", pose_residuals[0], pose_residuals[1],
                   pose_residuals[2], pose_residuals[3], Evaluate_GPUHC_Sols->success_flag ? "   ### Found GT pose!" : "");
     }
@@ -343,14 +391,22 @@ void GPU_HC_Solver::Free_Arrays_for_Aborting_RANSAC()
     delete[] h_Found_Trifocal_Sols[g]; h_Found_Trifocal_Sols[g] = nullptr;
     delete[] h_Trifocal_Sols_Batch_Index[g]; h_Trifocal_Sols_Batch_Index[g] = nullptr;
     delete h_best[g]; h_best[g] = nullptr;
-    cudaFree(d.d_edgels); cudaFree(d.d_found); cudaFree(d.d_found_index); cudaFree(d.d_K); cudaFree(d.d_best);
-    d.d_edgels = d.d_K = nullptr; d.d_found = nullptr; d.d_found_index = nullptr; d.d_best = nullptr;
+    cudaFree(d.d_found); cudaFree(d.d_found_index); cudaFree(d.d_best);
+    d.d_found = nullptr; d.d_found_index = nullptr; d.d_best = nullptr;
   }
   abort_arrays_allocated = false;
 }
 
 void GPU_HC_Solver::Free_Triplet_Edgels_Mem()
 {
+  if (device_edgels_allocated) {
+    for (int g = 0; g < Num_Of_GPUs; g++) {
+      cudaSetDevice(shard[g].device);
+      cudaFree(shard[g].d_edgels); cudaFree(shard[g].d_K);
+      shard[g].d_edgels = shard[g].d_K = nullptr;
+    }
+    device_edgels_allocated = false;
+  }
   if (!edgels_allocated) return;
   delete[] h_Triplet_Edge_Locations; delete[] h_Triplet_Edge_Tangents;
   h_Triplet_Edge_Locations = h_Triplet_Edge_Tangents = nullptr;
@@ -367,8 +423,8 @@ GPU_HC_Solver::~GPU_HC_Solver()
     cudaSetDevice(d.device);
     if (arrays_allocated) {
       cudaFree(d.d_start_sols); cudaFree(d.d_start_params); cudaFree(d.d_target); cudaFree(d.d_diff); cudaFree(d.d_tracks);
-      cudaFree(d.d_conv); cudaFree(d.d_inf); cudaFree(d.d_ws);
-      cudaFreeHost(h_Target_Params[g]); cudaFreeHost(h_diffParams[g]);
+      cudaFree(d.d_conv); cudaFree(d.d_inf); cudaFree(d.d_ws); cudaFree(d.d_support); cudaFree(d.d_score_best);
+      cudaFreeHost(h_Target_Params[g]); cudaFreeHost(h_diffParams[g]); cudaFreeHost(h_score_best[g]);
     }
     cudaEventDestroy((cudaEvent_t)d.ev_start); cudaEventDestroy((cudaEvent_t)d.ev_stop);
     cudaStreamDestroy((cudaStream_t)d.stream);

@@ -65,6 +65,8 @@ public:
   const std::vector<int>& Found_Path_Ids() const { return found_path_ids; }
   bool Found_Pose() const { return found_pose; }
   const std::array<float, 4>& Pose_Residuals() const { return pose_residuals; }         // R21, R31, t21, t31 vs ground truth
+  int Selected_Path() const { return selected_path; }                                   // global path id of the pose with maximal support
+  const std::array<unsigned, 2>& Selected_Support() const { return selected_support; }
   int Sub_RANSAC_Iters(int gpu_id) const { return sub_RANSAC_iters[gpu_id]; }
   void Set_Verbose(bool v) { verbose = v; }
   void Set_Pruning(bool on) { prune_paths = on; }       // the reference GPU kernels always prune (…TrunPaths.cu:148-154)
@@ -80,6 +82,8 @@ private:
     float *d_edgels = nullptr, *d_K = nullptr;
     int* d_found_index = nullptr;
     hcb200_best_record* d_best = nullptr;
+    int* d_support = nullptr;                 // [paths][2] inlier supports from hcb200_score_tracks
+    hcb200_best_record* d_score_best = nullptr;
     int path_offset = 0;     // first path of this shard in the stacked arrays
   };
   DeviceShard shard[MAX_NUM_OF_GPUS];
@@ -95,6 +99,7 @@ private:
   bool* h_Found_Trifocal_Sols[MAX_NUM_OF_GPUS] = {nullptr};
   int* h_Trifocal_Sols_Batch_Index[MAX_NUM_OF_GPUS] = {nullptr};
   hcb200_best_record* h_best[MAX_NUM_OF_GPUS] = {nullptr};
+  hcb200_best_record* h_score_best[MAX_NUM_OF_GPUS] = {nullptr};
   int* h_dHdx_Index = nullptr;          // parsed for format parity; the device code has the system compiled in
   int* h_dHdt_Index = nullptr;
   float* h_Camera_Intrinsic_Matrix = nullptr;
@@ -118,12 +123,16 @@ private:
   int sub_RANSAC_iters[MAX_NUM_OF_GPUS] = {0};
   bool arrays_allocated = false, abort_arrays_allocated = false, edgels_allocated = false;
   bool verbose = true, prune_paths = true;
+  bool device_scoring = true;       // final support counting + pose selection on the GPU (YAML key Device_Scoring)
+  bool device_edgels_allocated = false;
 
   std::vector<std::array<unsigned, 3>> per_hypothesis_counts;
   hcb200_best_record best_record{};
   std::vector<int> found_path_ids;
   bool found_pose = false;
   std::array<float, 4> pose_residuals{{100.f, 100.f, 100.f, 100.f}};
+  int selected_path = -1;
+  std::array<unsigned, 2> selected_support{{0u, 0u}};
 
   void check_multiGPUs();
   int device_of(int gpu_id) const { return (Num_Of_GPUs == 1) ? SET_GPU_DEVICE_ID : gpu_id; }

@@ -1,4 +1,5 @@
 // C handle API over GPU_HC_Solver (include/hcb200_host.h).
+#include <cmath>
 #include <cstring>
 #include <iostream>
 #include <sstream>
@@ -91,6 +92,13 @@ int hcb200_solver_best(hcb200_solver* s, hcb200_best_record* rec, int* pose_foun
   return 0;
 }
 
+int hcb200_solver_selected(hcb200_solver* s, int* path_id, unsigned support21_31[2])
+{
+  if (path_id) *path_id = s->impl->Selected_Path();
+  if (support21_31) { support21_31[0] = s->impl->Selected_Support()[0]; support21_31[1] = s->impl->Selected_Support()[1]; }
+  return s->impl->Found_Pose() ? 0 : 1;
+}
+
 int hcb200_solver_shard_size(hcb200_solver* s, int gpu_id) { return (gpu_id >= 0 && gpu_id < MAX_NUM_OF_GPUS) ? s->impl->Sub_RANSAC_Iters(gpu_id) : 0; }
 
 // ---- file-format access without a device (Data_Reader + the settings reader), used by the CPU-only tests ----------
@@ -114,6 +122,27 @@ int hcb200_reader_load(const char* problem_dir, const char* ransac_dir, int data
   if (!rd.Read_Intrinsic_Matrix(K)) return 8;
   rd.Read_Triplet_Edgels(locations, tangents);
   return 0;
+}
+
+// Host-side support of ONE end point with the Evaluations / mvg arithmetic (the reference's host scoring, per-solution):
+// returns 1 if the path is a pose candidate and fills the two inlier counts, 0 otherwise.  No device involved.
+int hcb200_host_score_track(const float* track31, const float* locations, int n_edgels, const float* K, int* n21, int* n31)
+{
+  namespace mvg = hcb200::mvg;
+  const hcb200::complex32* x = (const hcb200::complex32*)track31;
+  for (int vi = 24; vi < 30; vi++) if (!(std::fabs(x[vi].y) < IMAG_PART_TOL)) return 0;
+  for (int di = 0; di < 8; di++) if (!(x[di].x >= 0)) return 0;
+  const mvg::Vec3 t21 = mvg::normalized({x[18].x, x[19].x, x[20].x}), t31 = mvg::normalized({x[21].x, x[22].x, x[23].x});
+  const mvg::Mat3 R21 = mvg::cayley_to_rotation({x[24].x, x[25].x, x[26].x}), R31 = mvg::cayley_to_rotation({x[27].x, x[28].x, x[29].x});
+  int c21 = 0, c31 = 0;
+  for (int e = 0; e < n_edgels; e++) {
+    const float* g = locations + (size_t)e * 6;
+    const mvg::Vec3 g1 = {g[0], g[1], 1.0f}, g2 = {g[2], g[3], 1.0f}, g3 = {g[4], g[5], 1.0f};
+    if (mvg::reprojection_error_pixels(g1, g2, R21, t21, K, mvg::depth_rho(g1, g2, R21, t21)) < REPROJ_ERROR_INLIER_THRESH) c21++;
+    if (mvg::reprojection_error_pixels(g1, g3, R31, t31, K, mvg::depth_rho(g1, g3, R31, t31)) < REPROJ_ERROR_INLIER_THRESH) c31++;
+  }
+  *n21 = c21; *n31 = c31;
+  return 1;
 }
 
 int hcb200_settings_lookup(const char* settings_yaml, const char* key, char* out, int capacity)
