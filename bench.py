@@ -342,7 +342,13 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+                         "frac": achieved / fp32_peak if fp32_peak else None,
+                         "traffic": 206848, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum (0) of the tracker launch, "
+                                                              "ncu --set full capture v6 in profiles/ncu_r1.md; results stay in the 126 MB L2",
+                         "hbm": {"algorithmic_bytes_per_launch": H * (2 * 34 * 8) + n_paths * (31 * 8 + 2),
+                                 "achieved_gbs": (H * (2 * 34 * 8) + n_paths * (31 * 8 + 2)) / (ms_per_step * 1e-3) / 1e9,
+                                 "peak_gbs": 6553.0, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
+                                 "note": "the path is not HBM-bound: 78 KB and ~8 Gflop (model) per hypothesis"},
                          "peak_source": "FFMA probe kernel timed live on this GPU (MEASURED_PEAKS.json has no FP32 entry); "
                                         "nominal 148x128x2x1.965GHz = %.1f" % NOMINAL_FP32_TFLOPS,
                          "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS,
