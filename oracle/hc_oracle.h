@@ -12,8 +12,10 @@
  *   early-abort scoring ... magmaHC/dev-trifocal_2op1p-eval.cuh:28-250
  *   hypothesis sampling ... magmaHC/GPU_HC_Solver.cpp:252-306
  * with ONE fixed floating-point evaluation order ("the arithmetic spec") that the CUDA kernels follow
- * operation for operation, so kernel and oracle agree bit for bit.  The oracle itself is pinned against the real
- * reference (oracle/_ref, built from /root/reference) by tests/test_oracle_vs_reference.py and tests/golden/.
+ * operation for operation, so kernel and oracle agree bit for bit.  PINNING: the oracle is checked against outputs of the
+ * real reference run in the build container (oracle/_ref/libref_cpuhc.so, built from /root/reference; goldens in tests/golden/
+ * made by tools/make_golden.py) and against the known answers of SURVEY.md App. C — tests/test_oracle.py.  Unpinned: the
+ * arithmetic of MAGMA's complex operators and of OpenBLAS cgesv, whose sources are not part of the reference tree.
  */
 #ifndef HC_ORACLE_H
 #define HC_ORACLE_H
