@@ -87,3 +87,88 @@ def test_device_target_params_match_host(tracker, oracle, ransac0):
     assert np.array_equal(p2, picked)
     t2, d2 = hc.target_params_from_picks(p2, ransac0["locations"], ransac0["tangents"], oracle.start_params)
     assert np.array_equal(t2, target) and np.array_equal(d2, diff)
+
+
+def _assert_same(tracker, oracle, target, diff, prune):
+    n_hyp = target.shape[0]
+    tr_o, cv_o, inf_o, st_o = oracle.track(target, diff, prune)
+    tracker.upload_params(target, diff)
+    tracker.track(n_hyp, prune=prune)
+    tr_g, cv_g, inf_g, st_g = tracker.results(n_hyp)
+    assert np.array_equal(cv_g, cv_o) and np.array_equal(inf_g, inf_o)
+    assert np.array_equal(st_g[:, :3], st_o[:, :3])
+    assert np.array_equal(st_g[:, 3] & 0xffff, st_o[:, 3]) and np.array_equal(st_g[:, 3] >> 16, st_o[:, 4])
+    assert _bit_equal(tr_g[:, :30], tr_o[:, :30])
+    return tr_g, cv_g, inf_g, st_g
+
+
+@pytest.mark.parametrize("dataset", [1, 2, 3])
+def test_other_datasets_bit_exact(tracker, oracle, dataset):
+    """RANSAC_Data/Synthetic/001-003 (SURVEY.md §8d config 5 draws hypotheses from the other dataset files)."""
+    from trifocal_pose_estimation_using_improved_gpuhc_b200 import fixtures
+    rs = fixtures.load_ransac(dataset)
+    target, diff, _ = oracle.prepare_target_params(dataset, 2, rs["locations"], rs["tangents"])
+    _assert_same(tracker, oracle, target, diff, True)
+
+
+@pytest.mark.parametrize("prune", [True, False])
+def test_random_complex_targets_bit_exact(tracker, oracle, prune):
+    """Second input distribution of SURVEY.md §8d config 5: target = U(0,1) + i U(0,1) (the reference's Julia start-system
+    script draws its parameters this way).  Generic complex targets keep almost every path alive to the step cap or send it
+    to infinity, so this exercises the long-path, overflow and NaN branches that edgel-derived (real) targets rarely reach."""
+    rng = np.random.default_rng(20240607)
+    n_hyp = 2
+    target = np.zeros((n_hyp, 34), np.complex64)
+    target[:, :33] = (rng.random((n_hyp, 33)) + 1j * rng.random((n_hyp, 33))).astype(np.complex64)
+    target[:, 33] = 1.0
+    diff = (target - oracle.start_params[None, :]).astype(np.complex64)
+    diff[:, 33] = 0.0
+    tr_g, cv_g, inf_g, st_g = _assert_same(tracker, oracle, target, diff, prune)
+    assert st_g[:, 0].max() >= 40          # long paths were exercised
+
+
+def test_degenerate_targets_bit_exact(tracker, oracle):
+    """target == start (zero parameter velocity: every predictor stage solves A k = 0), an all-zero target (singular Jacobians,
+    zero pivots), a huge target (overflow -> the infinity exit) and NaN / Inf parameters (NaN pivot keys and norms)."""
+    start = oracle.start_params.astype(np.complex64)
+    target = np.zeros((5, 34), np.complex64)
+    target[0] = start
+    target[2, :33] = np.complex64(3.0e18 + 1.0e18j)
+    target[3] = start
+    target[3, 5] = np.complex64(complex(np.nan, 0.0))          # NaN parameter: NaN pivots, NaN norms
+    target[4] = start
+    target[4, 7] = np.complex64(complex(np.inf, 0.0))          # Inf parameter
+    target[:, 33] = 1.0
+    diff = (target - start[None, :]).astype(np.complex64)
+    diff[:, 33] = 0.0
+    tr_g, cv_g, inf_g, st_g = _assert_same(tracker, oracle, target, diff, False)
+    # target == start: the start solutions already solve the system; every path runs to t = 1 and converges where it began
+    assert cv_g[:312].all()
+
+
+def test_abort_late_hit(tracker, oracle, ransac0):
+    """SURVEY.md §8d config 3, second half: a sampler seed whose first passing pose comes late in the round (seed 13: hypothesis
+    30, path 9606 — found with tools/find_abort_seeds.py).  The oracle tracks and scores all 40 hypotheses; the abort launch must
+    flag only paths the oracle also passes, none before the oracle's first, and must skip the work queued behind the flag."""
+    n_hyp = 40
+    loc, K = ransac0["locations"], ransac0["K"]
+    target, diff, _ = oracle.prepare_target_params(13, n_hyp, loc, ransac0["tangents"])
+    tr_o, cv_o, inf_o, st_o = oracle.track(target, diff, True)
+    passing = [int(b) for b in np.nonzero(cv_o)[0] if oracle.score(tr_o[b], loc, K)[0]]
+    assert passing and min(passing) == 9606
+    tracker.set_edgels(loc, K)
+    tracker.upload_params(target, diff)
+    tracker.track_abort(n_hyp, prune=True)
+    tr_g, cv_g, inf_g, st_g = tracker.results(n_hyp)
+    idx = tracker.d_found_index[: n_hyp * 312].cpu().numpy()
+    best = tracker.d_best.cpu().numpy()
+    hits = np.nonzero(idx >= 0)[0]
+    assert int(tracker.d_found.cpu()[0]) == 1 and len(hits) >= 1
+    assert set(hits.tolist()) <= set(passing)
+    assert best[0] == 1 and best[1] == hits.min() and best[4] == len(hits)
+    for b in hits:                                   # a flagged path ran to completion: same end point as the oracle, bit for bit
+        assert _bit_equal(tr_g[b, :30], tr_o[b, :30])
+    reason = st_g[:, 3] >> 16
+    assert (reason == 4).sum() > 0                   # work behind the flag was skipped
+    done = reason < 4                                # paths that finished before the flag are the oracle's, bit for bit
+    assert np.array_equal(cv_g[done], cv_o[done]) and _bit_equal(tr_g[done][:, :30], tr_o[done][:, :30])
