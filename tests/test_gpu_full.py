@@ -200,6 +200,32 @@ def test_hc_main_writes_reference_output_files(tree):
     assert len(timing) == 1 and 0 < float(timing[0]) < 5000
 
 
+DROPIN = os.path.join(ROOT, "oracle", "_ref", "ref_gpuhc_on_hcb200")
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN), reason="oracle/_ref/ref_gpuhc_on_hcb200 not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("abort", [False, True])
+def test_unmodified_reference_host_layer_runs_on_this_library(tmp_path, abort):
+    """The drop-in claim itself: the reference's OWN GPU_HC_Solver.cpp / Data_Reader.cpp / Evaluations.cpp (compiled unmodified
+    from /root/reference in the build container) linked against integration/hcb200_shim.cpp + libhcb200.so instead of the
+    reference kernels.  The statistics file the reference writes must carry the golden counts of the default round."""
+    root = str(tmp_path)
+    fixtures.materialize_tree(root, files=[0], settings_overrides={"Abort_RANSAC_by_Good_Sol": "true"} if abort else None)
+    out = subprocess.run([DROPIN, "trifocal_2op1p_30x30", "100"], cwd=os.path.join(root, "build", "bin"),
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "Number of Converged Solutions" in out.stdout
+    stats = [int(v) for v in open(os.path.join(root, "Output_Write_Files", "GPU_Sols_Statistics.txt")).read().split()]
+    g = np.load(os.path.join(GOLD, "oracle_seed0_h100_prune.npz"))
+    c = g["counts"].sum(0)                                    # conv, inf, real
+    if not abort:
+        assert stats == [int(c[0]), int(c[2]), int(c[1])], (stats, out.stdout[-1500:])     # converged, real, infinity (App. A.4)
+    else:
+        assert 1 <= stats[0] < int(c[0])                      # the flag stopped the round early
+    ms = float(open(os.path.join(root, "Output_Write_Files", "GPU_Timings.txt")).read().split()[0])
+    assert 0 < ms < 1000
+
+
 def test_host_class_two_gpus_same_answer(tree):
     import torch
     if torch.cuda.device_count() < 2:
