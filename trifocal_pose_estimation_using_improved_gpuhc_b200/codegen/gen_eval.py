@@ -82,6 +82,33 @@ def parse_terms(hx, ht):
     return hx_terms, h_terms
 
 
+def superstep_shared_columns(hx_terms, K1, segments, seg_cols):
+    """For every super-step T of the sparse phase: the lowest shared (dense) column that can be structurally non-zero in ANY
+    row taking part in it (candidates and rows being swept, fill-in included, every pivot choice allowed).  Shared columns
+    below it are exact zeros in all those rows, so the step neither ships nor updates them."""
+    P = np.zeros((N, N), bool)
+    for (r, c) in hx_terms:
+        P[r, c] = True
+    nsp = max(len(c) for c in seg_cols)
+    first = []
+    for T in range(nsp):
+        need = np.zeros(N, bool)
+        for seg, cols in zip(segments, seg_cols):
+            if T >= len(cols):
+                continue
+            c = cols[T]
+            part = [r for r in seg if P[r, c]]
+            u = np.zeros(N, bool)
+            for r in part:
+                u |= P[r]
+            for r in part:
+                P[r] |= u
+            need |= u
+        shared = [c for c in range(K1, N) if need[c]]
+        first.append(min(shared) if shared else N)
+    return first
+
+
 def column_classes(hx_terms):
     """Greedy colouring: two columns may share a class iff no row has a non-zero in both."""
     rows_of = {c: {r for (r, cc) in hx_terms if cc == c} for c in range(N)}
@@ -238,6 +265,7 @@ def build():
 
     # ---- block structure -> lane permutation and register slots -------------------------------------------
     K1, segments, seg_cols = analyze_blocks(hx_terms)
+    sp_first_shared = superstep_shared_columns(hx_terms, K1, segments, seg_cols)
     SEG = 6
     row_of_lane = [-1] * WARP
     for g, seg in enumerate(segments):
@@ -372,7 +400,7 @@ def build():
     return dict(hx_terms=hx_terms, h_terms=h_terms, cq_list=cq_list, dq_list=dq_list, classes=classes,
                 col_class=col_class, hx_slots=hx_slots, h_slots=h_slots, ht_slots=ht_slots,
                 K1=K1, segments=segments, seg_cols=seg_cols, row_of_lane=row_of_lane, lane_of_row=lane_of_row,
-                nsp=nsp, nd=nd, nslot=nslot, scatter=scatter, sel_of_lane=sel_of_lane, nz_of_lane=nz_of_lane, n_sel=n_sel,
+                nsp=nsp, nd=nd, nslot=nslot, sp_first_shared=sp_first_shared, scatter=scatter, sel_of_lane=sel_of_lane, nz_of_lane=nz_of_lane, n_sel=n_sel,
                 pairs=pair_by_pos, triples=tri_by_pos, XP_PAIR0=XP_PAIR0, XP_TRI0=XP_TRI0, XP_TOTAL=XP_TOTAL,
                 layout_cost=layout_cost)
 
@@ -473,6 +501,8 @@ def emit(g, path):
     w("#define HCG_NSLOT %d     /* register slots per row */" % g["nslot"])
     w("#define HCG_SEG 6")
     w("#define HCG_NSEG %d" % len(g["segments"]))
+    w("// per super-step: first register slot of the shared columns that can be non-zero in a participating row")
+    w("#define HCG_SP_FIRST_SHARED_SLOT_INIT { " + ",".join(str(g["nsp"] + c - g["K1"]) for c in g["sp_first_shared"]) + " }")
     w("#define HCG_ROW_OF_LANE_INIT { " + ",".join(str(r) for r in g["row_of_lane"]) + " }")
     w("#define HCG_LANE_OF_ROW_INIT { " + ",".join(str(r) for r in g["lane_of_row"]) + " }")
     # per-lane info word: nz mask over slots (bits 0..nslot-1) | selector bits << 20 | number of sparse columns << 24
