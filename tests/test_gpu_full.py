@@ -204,13 +204,19 @@ DROPIN = os.path.join(ROOT, "oracle", "_ref", "ref_gpuhc_on_hcb200")
 
 
 @pytest.mark.skipif(not os.path.exists(DROPIN), reason="oracle/_ref/ref_gpuhc_on_hcb200 not built (needs /root/reference at build time)")
-@pytest.mark.parametrize("abort", [False, True])
-def test_unmodified_reference_host_layer_runs_on_this_library(tmp_path, abort):
+@pytest.mark.parametrize("abort,n_gpus", [(False, 1), (True, 1), (False, 2)])
+def test_unmodified_reference_host_layer_runs_on_this_library(tmp_path, abort, n_gpus):
     """The drop-in claim itself: the reference's OWN GPU_HC_Solver.cpp / Data_Reader.cpp / Evaluations.cpp (compiled unmodified
     from /root/reference in the build container) linked against integration/hcb200_shim.cpp + libhcb200.so instead of the
     reference kernels.  The statistics file the reference writes must carry the golden counts of the default round."""
+    import torch
+    if torch.cuda.device_count() < n_gpus:
+        pytest.skip("needs %d GPUs" % n_gpus)
     root = str(tmp_path)
-    fixtures.materialize_tree(root, files=[0], settings_overrides={"Abort_RANSAC_by_Good_Sol": "true"} if abort else None)
+    ov = {"Num_Of_GPUs": str(n_gpus)}
+    if abort:
+        ov["Abort_RANSAC_by_Good_Sol"] = "true"
+    fixtures.materialize_tree(root, files=[0], settings_overrides=ov)
     out = subprocess.run([DROPIN, "trifocal_2op1p_30x30", "100"], cwd=os.path.join(root, "build", "bin"),
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]

@@ -23,11 +23,22 @@ using hcb200::complex32;
     }                                                                                                       \
   } while (0)
 
+namespace {
+// Every public method that walks over the shards leaves the caller's current device as it found it (the reference's
+// magma_setdevice loops do not, GPU_HC_Solver.cpp:392; a library living inside someone else's process should).
+struct DeviceGuard {
+  int saved = -1;
+  DeviceGuard() { if (cudaGetDevice(&saved) != cudaSuccess) saved = -1; }
+  ~DeviceGuard() { if (saved >= 0) cudaSetDevice(saved); }
+};
+}  // namespace
+
 static double wall_seconds()
 { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 GPU_HC_Solver::GPU_HC_Solver(YAML::Node cfg) : Problem_Setting_YAML_File(cfg)
 {
+  DeviceGuard keep_callers_device;
   HC_problem                      = cfg["problem_name"].as<std::string>();
   HC_print_problem_name           = cfg["problem_print_out_name"].as<std::string>();
   GPUHC_Max_Steps                 = cfg["GPUHC_Max_Steps"].as<int>();
@@ -99,6 +110,7 @@ void GPU_HC_Solver::check_multiGPUs()
 
 void GPU_HC_Solver::Allocate_Arrays()
 {
+  DeviceGuard keep_callers_device;
   const size_t V1 = Num_Of_Vars + 1, P1 = Num_Of_Params + 1, n_paths = (size_t)Num_Of_Paths();
   h_Start_Sols   = (complex32*)std::malloc(sizeof(complex32) * Num_Of_Tracks * V1);
   h_Start_Params = (complex32*)std::malloc(sizeof(complex32) * P1);
@@ -182,6 +194,7 @@ void GPU_HC_Solver::Prepare_Target_Params(unsigned rand_seed_)
 
 void GPU_HC_Solver::Set_RANSAC_Abort_Arrays()
 {
+  DeviceGuard keep_callers_device;
   if (!Abort_RANSAC_by_Good_Sol) return;
   for (int g = 0; g < Num_Of_GPUs; g++) {
     DeviceShard& d = shard[g];
@@ -201,6 +214,7 @@ void GPU_HC_Solver::Set_RANSAC_Abort_Arrays()
 
 void GPU_HC_Solver::Data_Transfer_From_Host_To_Device()
 {
+  DeviceGuard keep_callers_device;
   const size_t V1 = Num_Of_Vars + 1, P1 = Num_Of_Params + 1;
   for (int g = 0; g < Num_Of_GPUs; g++) {
     DeviceShard& d = shard[g];
@@ -238,6 +252,7 @@ void GPU_HC_Solver::Set_CUDA_Stream_Attributes() {}
 
 void GPU_HC_Solver::Solve_by_GPU_HC()
 {
+  DeviceGuard keep_callers_device;
   if (verbose) std::cout << "GPU computing ..." << std::endl << std::endl;
   const unsigned flags = prune_paths ? HCB200_FLAG_PRUNE_PATHS : 0u;
   const size_t V1 = Num_Of_Vars + 1;
@@ -384,6 +399,7 @@ void GPU_HC_Solver::Export_Data() {}
 
 void GPU_HC_Solver::Free_Arrays_for_Aborting_RANSAC()
 {
+  DeviceGuard keep_callers_device;
   if (!abort_arrays_allocated) return;
   for (int g = 0; g < Num_Of_GPUs; g++) {
     DeviceShard& d = shard[g];
@@ -399,6 +415,7 @@ void GPU_HC_Solver::Free_Arrays_for_Aborting_RANSAC()
 
 void GPU_HC_Solver::Free_Triplet_Edgels_Mem()
 {
+  DeviceGuard keep_callers_device;
   if (device_edgels_allocated) {
     for (int g = 0; g < Num_Of_GPUs; g++) {
       cudaSetDevice(shard[g].device);
@@ -415,6 +432,7 @@ void GPU_HC_Solver::Free_Triplet_Edgels_Mem()
 
 GPU_HC_Solver::~GPU_HC_Solver()
 {
+  DeviceGuard keep_callers_device;
   Free_Arrays_for_Aborting_RANSAC();
   Free_Triplet_Edgels_Mem();
   for (int g = 0; g < Num_Of_GPUs && g < MAX_NUM_OF_GPUS; g++) {
