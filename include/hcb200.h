@@ -101,6 +101,15 @@ int hcb200_score_tracks(void* stream, int n_paths, const float* d_tracks, const 
                         const float* d_edgel_locations, const float* d_intrinsic, int32_t* d_support,
                         hcb200_best_record* d_best, void* d_workspace);
 
+/* Newton refinement of converged end points on the device (next row of SURVEY.md §8f-3; the reference has no such kernel — it is
+ * what Evaluations::Find_Unique_Sols, reference Evaluations.cpp:184-233, needs before end points can be compared at
+ * DUPLICATE_SOL_DIFF_TOL = 1e-4).  For every path with d_converged[path] != 0: n_iters Newton corrector iterations
+ * x -= Hx(x, target)^-1 H(x, target) against the path's TARGET system (hypothesis = path / 312), evaluators and 30x30 solve of the
+ * tracker (same arithmetic spec).  d_tracks is updated in place; d_sums[2*path + {0,1}] = sum |dx|^2 and sum |x|^2 of the last
+ * iteration (the tracker's convergence test is sum|dx|^2 < 1e-6 sum|x|^2), or -1, -1 for paths that were not refined. */
+int hcb200_refine_tracks(void* stream, int n_paths, int n_iters, const float* d_target_params, const uint8_t* d_converged,
+                         float* d_tracks, float* d_sums, void* d_workspace);
+
 /* Introspection for benchmarks/tests: registers per thread, static+dynamic shared bytes per CTA, resident CTAs per SM,
  * grid size a launch would use on the current device.  Any pointer may be NULL. */
 int hcb200_kernel_info(int abort_variant, int* regs, int* smem_bytes, int* ctas_per_sm, int* grid, int* block);

@@ -457,6 +457,33 @@ static inline zc z_add(zc a, zc b) { zc r = {a.re + b.re, a.im + b.im}; return r
 static inline zc z_div(zc a, zc b)
 { double d = b.re * b.re + b.im * b.im; zc r = {(a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d}; return r; }
 
+/* Newton refinement in the arithmetic spec (float): what hcb200_refine_tracks does on the device.  x31 in/out. */
+void hco_refine_path(const int* dHdx, const int* dHdt, const hco_c32* target34, hco_c32* x31, int iters, float* out_sum_d, float* out_sum_x)
+{
+  hco_c32 x[HCO_N + 1], p[HCO_NP + 1], A[HCO_N * HCO_N], b[HCO_N];
+  memcpy(x, x31, sizeof(hco_c32) * HCO_N);
+  x[HCO_N] = c_make(1.0f, 0.0f);
+  memcpy(p, target34, sizeof p);
+  float sum_d = -1.0f, sum_x = -1.0f;
+  for (int it = 0; it < iters; it++) {
+    hco_eval_Hx(dHdx, x, p, A);
+    hco_eval_H(dHdt, x, p, b);
+    hco_solve(A, b);
+    float vd[HCO_N], vx[HCO_N];
+    for (int i = 0; i < HCO_N; i++) {
+      x[i] = c_sub(x[i], b[i]);
+      vd[i] = fmaf(b[i].re, b[i].re, b[i].im * b[i].im);
+      vx[i] = fmaf(x[i].re, x[i].re, x[i].im * x[i].im);
+    }
+    sum_d = butterfly_sum(vd);
+    sum_x = butterfly_sum(vx);
+  }
+  memcpy(x31, x, sizeof(hco_c32) * HCO_N);
+  *out_sum_d = sum_d;
+  *out_sum_x = sum_x;
+}
+
+
 double hco_newton_refine_f64(const int* dHdx, const int* dHdt, const hco_c32* tp, const hco_c32* x_in, int iters, double* x_out)
 {
   zc x[HCO_N + 1], p[HCO_NP + 1], A[HCO_N][HCO_N], b[HCO_N];

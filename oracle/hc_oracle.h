@@ -81,6 +81,10 @@ void hco_prepare_target_params(unsigned seed, int n_hyp, int n_edgels, const flo
 double hco_newton_refine_f64(const int* dHdx, const int* dHdt, const hco_c32* target34, const hco_c32* x31_in,
                              int iters, double* x_out_re_im /*[30][2]*/);
 
+/* Newton refinement in float, in the arithmetic spec (the oracle of hcb200_refine_tracks): `iters` corrector iterations against the
+ * target system; x31 in/out; sums = sum|dx|^2, sum|x|^2 of the last iteration (-1 when iters == 0). */
+void hco_refine_path(const int* dHdx, const int* dHdt, const hco_c32* target34, hco_c32* x31, int iters, float* out_sum_d, float* out_sum_x);
+
 #ifdef __cplusplus
 }
 #endif

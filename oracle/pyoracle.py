@@ -118,6 +118,13 @@ class Oracle:
                                          ctypes.byref(gate))
         return bool(ok), n21.value, n31.value, bool(gate.value)
 
+    def refine(self, target34, x31, iters=3):
+        """Float Newton refinement in the arithmetic spec (oracle of hcb200_refine_tracks): returns x31 (copy), sum_d, sum_x."""
+        x = np.ascontiguousarray(c2f(np.asarray(x31, np.complex64).copy()))
+        sd, sx = ctypes.c_float(), ctypes.c_float()
+        self.lib.hco_refine_path(_vp(self.hx), _vp(self.ht), _vp(c2f(target34)), _vp(x), int(iters), ctypes.byref(sd), ctypes.byref(sx))
+        return f2c(x), sd.value, sx.value
+
     def newton_refine(self, target34, x31, iters=6):
         out = np.zeros((N, 2), np.float64)
         res = self.lib.hco_newton_refine_f64(_vp(self.hx), _vp(self.ht), _vp(c2f(target34)), _vp(c2f(x31)), iters, _vp(out))

@@ -175,6 +175,24 @@ def test_host_class_default_round_matches_golden(tree):
     assert np.array_equal(r2["residuals"], r["residuals"])
 
 
+def test_host_class_refinement_option(tree):
+    """Refine_Iterations = 3 (optional YAML key): converged end points are polished on the GPU before they are copied back;
+    flags and counts are untouched, the selected pose is the same, and duplicates of one root now agree far below the
+    reference's DUPLICATE_SOL_DIFF_TOL (Evaluations.cpp:184-233)."""
+    s = HostSolver(tree, "Num_Of_GPUs=1;Num_Of_RANSAC_Iterations=10")
+    r0 = s.round()
+    s.close()
+    s = HostSolver(tree, "Num_Of_GPUs=1;Num_Of_RANSAC_Iterations=10;Refine_Iterations=3")
+    r1 = s.round()
+    s.close()
+    assert np.array_equal(r0["conv"], r1["conv"]) and np.array_equal(r0["inf"], r1["inf"])
+    assert r1["selected_path"] == r0["selected_path"] == 104 and r1["pose_found"] == 1
+    conv = r0["conv"] == 1
+    moved = np.abs(r1["tracks"][conv, :30] - r0["tracks"][conv, :30]).max(axis=1) / np.maximum(1.0, np.abs(r0["tracks"][conv, :30]).max(axis=1))
+    assert np.median(moved) < 1e-3 and (moved > 0).mean() > 0.5           # a polish, not a different answer
+    assert np.array_equal(r1["tracks"][~conv], r0["tracks"][~conv])       # paths that did not converge are left alone
+
+
 def test_host_class_early_abort_finds_gt_pose(tree):
     s = HostSolver(tree, "Num_Of_GPUs=1;Abort_RANSAC_by_Good_Sol=true")
     r = s.round()

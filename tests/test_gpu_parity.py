@@ -172,3 +172,30 @@ def test_abort_late_hit(tracker, oracle, ransac0):
     assert (reason == 4).sum() > 0                   # work behind the flag was skipped
     done = reason < 4                                # paths that finished before the flag are the oracle's, bit for bit
     assert np.array_equal(cv_g[done], cv_o[done]) and _bit_equal(tr_g[done][:, :30], tr_o[done][:, :30])
+
+
+def test_device_refinement_bit_exact_vs_oracle(tracker, oracle, ransac0):
+    """hcb200_refine_tracks: Newton refinement of converged end points against their target systems, same arithmetic spec as the
+    tracker's corrector -> bit-identical to the oracle's hco_refine_path; paths that did not converge are left alone."""
+    n_hyp = 3
+    target, diff, _ = oracle.prepare_target_params(0, n_hyp, ransac0["locations"], ransac0["tangents"])
+    tracker.upload_params(target, diff)
+    tracker.track(n_hyp, prune=True)
+    tr0, cv, inf, _ = tracker.results(n_hyp)
+    sums = tracker.refine_tracks(n_hyp, iters=3)
+    tr1, cv1, _, _ = tracker.results(n_hyp)
+    assert np.array_equal(cv, cv1)
+    not_conv = cv == 0
+    assert _bit_equal(tr1[not_conv], tr0[not_conv]) and np.all(sums[not_conv] == -1.0)
+    conv = np.nonzero(cv)[0]
+    assert len(conv) > 50
+    for b in conv:
+        x, sd, sx = oracle.refine(target[b // 312], tr0[b], iters=3)
+        assert _bit_equal(tr1[b, :30], x[:30]), b
+        assert _bit_equal(np.array([sd, sx], np.float32), sums[b]), b
+    # the ground-truth pose (hypothesis 0 / track 104) is a regular solution: the polish settles at the float floor
+    assert sums[104, 0] < 1e-9 * sums[104, 1]
+    # iters = 0: nothing moves
+    tracker.refine_tracks(n_hyp, iters=0)
+    tr2, _, _, _ = tracker.results(n_hyp)
+    assert _bit_equal(tr2, tr1)

@@ -164,6 +164,19 @@ def test_endpoints_agree_after_newton_refinement(oracle, first6):
     assert n_same >= 0.95 * n_cmp
 
 
+def test_float_refinement_polishes_regular_end_points(oracle, first6):
+    """hco_refine_path (the oracle of hcb200_refine_tracks): three float Newton iterations at t = 1 take the ground-truth track to
+    the root the double-precision polish finds, to float accuracy; zero iterations change nothing."""
+    g, tgt, tr, cv, inf, st = first6
+    x3, sd, sx = oracle.refine(tgt[0], tr[104], iters=3)
+    x64, res = oracle.newton_refine(tgt[0], tr[104], iters=8)
+    assert res < 1e-10
+    assert np.abs(x3[:30] - x64).max() / np.abs(x64).max() < 5e-6
+    assert 0 <= sd < 1e-9 * sx          # float floor: |dx| ~ eps * cond * |x|
+    x0, sd0, sx0 = oracle.refine(tgt[0], tr[104], iters=0)
+    assert np.array_equal(x0, tr[104]) and (sd0, sx0) == (-1.0, -1.0)
+
+
 def test_gt_pose_is_found_and_scores_full_support(oracle, first6, ransac0):
     """hypothesis 0 / track 104 is the ground-truth pose with 5117/5117 inliers in both view pairs."""
     from trifocal_pose_estimation_using_improved_gpuhc_b200 import fixtures

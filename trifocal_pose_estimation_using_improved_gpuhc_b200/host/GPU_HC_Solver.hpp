@@ -84,6 +84,7 @@ private:
     hcb200_best_record* d_best = nullptr;
     int* d_support = nullptr;                 // [paths][2] inlier supports from hcb200_score_tracks
     hcb200_best_record* d_score_best = nullptr;
+    float* d_refine_sums = nullptr;           // [paths][2] from hcb200_refine_tracks (only with Refine_Iterations > 0)
     int path_offset = 0;     // first path of this shard in the stacked arrays
   };
   DeviceShard shard[MAX_NUM_OF_GPUS];
@@ -124,6 +125,8 @@ private:
   bool arrays_allocated = false, abort_arrays_allocated = false, edgels_allocated = false;
   bool verbose = true, prune_paths = true;
   bool device_scoring = true;       // final support counting + pose selection on the GPU (YAML key Device_Scoring)
+  int refine_iterations = 0;        // Newton refinement of converged end points on the GPU before they are copied back
+                                    // (YAML key Refine_Iterations; 0 = the reference's behaviour)
   bool device_edgels_allocated = false;
 
   std::vector<std::array<unsigned, 3>> per_hypothesis_counts;
