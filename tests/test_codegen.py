@@ -78,11 +78,14 @@ def test_schedule_covers_every_term_once_in_table_order():
 
 
 def test_block_structure_is_what_the_kernel_assumes():
-    """analyze_blocks: 18 sparse pivot columns in five independent 6-row groups, 12 shared columns, 17 register slots."""
+    """analyze_blocks + level_schedule: 18 sparse pivot columns in five independent 6-row groups, scheduled on 4 levels (columns of a
+    group whose rows are disjoint share a level), 12 shared columns, 16 register slots."""
     g = gen_eval.build()
-    assert g["K1"] == 18 and g["nsp"] == 5 and g["nd"] == 12 and g["nslot"] == 17
+    assert g["K1"] == 18 and g["nsp"] == 4 and g["nd"] == 12 and g["nslot"] == 16
     assert g["segments"] == [[3, 4, 5, 12, 13, 14], [6, 7, 8, 15, 16, 17], [0, 1, 2, 9, 10, 11], [18, 19, 20, 24, 25, 26], [21, 22, 23, 27, 28, 29]]
     assert g["seg_cols"] == [[0, 3, 6], [1, 4, 7], [2, 5], [8, 9, 12, 13, 14], [10, 11, 15, 16, 17]]
+    assert [sorted(c for (_, c, _) in lv) for lv in g["levels"]] == [[0, 1, 2, 5, 8, 9, 10, 11], [3, 4, 12, 15], [6, 7, 13, 16], [14, 17]]
+    assert g["sp_first_shared"] == [18, 18, 18, 24] and g["max_sub"] == 2
     # every structural non-zero of a row is in one of the row's slots, and rows are ascending inside a segment
     for lane, row in enumerate(g["row_of_lane"]):
         if row < 0:
@@ -90,7 +93,7 @@ def test_block_structure_is_what_the_kernel_assumes():
         seg = lane // 6
         for c in range(30):
             if (row, c) in g["hx_terms"]:
-                assert c >= g["K1"] or c in g["seg_cols"][seg]
+                assert c >= g["K1"] or (c in g["seg_cols"][seg] and g["col_at"][lane][g["level_of_col"][c]] == c)
     for seg in g["segments"]:
         assert seg == sorted(seg)
     # independence that makes the block-parallel schedule exact: a sparse column is non-zero only inside its own segment
@@ -98,6 +101,39 @@ def test_block_structure_is_what_the_kernel_assumes():
         if c < g["K1"]:
             owner = [i for i, cols in enumerate(g["seg_cols"]) if c in cols][0]
             assert row in g["segments"][owner]
+
+
+def test_level_schedule_is_exact():
+    """Replays a symbolic natural-order elimination with worst-case fill-in and checks what the levels rely on: the groups of one
+    level have pairwise disjoint rows, a column's level is above the level of every earlier column that shares a row with it, and a
+    row's entry in a column it does not 'meet' stays structurally zero (so leaving it out of that column's pivot search and update
+    changes nothing)."""
+    g = gen_eval.build()
+    P = np.zeros((30, 30), bool)
+    for (r, c) in g["hx_terms"]:
+        P[r, c] = True
+    part_of = {}
+    for lv in g["levels"]:
+        rows = [r for (_, _, part) in lv for r in part]
+        assert len(rows) == len(set(rows))
+        for (_, c, part) in lv:
+            part_of[c] = part
+    assert sorted(part_of) == list(range(g["K1"]))
+    last_level = {}
+    for c in range(g["K1"]):                                  # natural order, as the oracle eliminates
+        touched = [r for r in range(30) if P[r, c]]
+        assert sorted(touched) == sorted(part_of[c])          # exactly the rows of the group: everything else is structurally zero
+        u = np.zeros(30, bool)
+        for r in touched:
+            u |= P[r]
+        for r in touched:
+            P[r] |= u
+            assert last_level.get(r, -1) < g["level_of_col"][c]
+            last_level[r] = g["level_of_col"][c]
+    # rows taking part in the last level never touch shared columns 18..23
+    for (_, c, part) in g["levels"][-1]:
+        for r in part:
+            assert not P[r, 18:24].any()
 
 
 def test_column_classes_partition_the_nonzero_columns():

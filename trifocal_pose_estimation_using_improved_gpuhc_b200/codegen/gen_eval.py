@@ -82,31 +82,48 @@ def parse_terms(hx, ht):
     return hx_terms, h_terms
 
 
-def superstep_shared_columns(hx_terms, K1, segments, seg_cols):
-    """For every super-step T of the sparse phase: the lowest shared (dense) column that can be structurally non-zero in ANY
-    row taking part in it (candidates and rows being swept, fill-in included, every pivot choice allowed).  Shared columns
-    below it are exact zeros in all those rows, so the step neither ships nor updates them."""
+def level_schedule(hx_terms, K1, segments, seg_cols):
+    """Schedule of the sparse phase.  Inside a segment, two private pivot columns commute exactly when no row takes part in both
+    (a row takes part in a column's step when its entry there can be non-zero, fill-in included, every pivot choice allowed), so
+    columns are put on LEVELS: level(c) = 1 + the last level any of c's rows was busy in, walking the columns in natural order.
+    One level of all segments is one super-step of the kernel; within a segment a level holds one or more GROUPS = (column,
+    rows) with disjoint row sets, each with its own pivot search and pivot row.
+    Returns (levels, level_of_col, first_shared): levels[T] = list of (segment, column, rows); first_shared[T] = the lowest
+    shared column that can be non-zero in any row taking part in level T (shared columns below it are exact zeros in all of
+    them, so that super-step neither ships nor updates them)."""
     P = np.zeros((N, N), bool)
     for (r, c) in hx_terms:
         P[r, c] = True
-    nsp = max(len(c) for c in seg_cols)
-    first = []
-    for T in range(nsp):
-        need = np.zeros(N, bool)
-        for seg, cols in zip(segments, seg_cols):
-            if T >= len(cols):
-                continue
-            c = cols[T]
+    level_of_col = {}
+    groups = []                                   # (level, segment, column, rows, union pattern)
+    for g, (seg, cols) in enumerate(zip(segments, seg_cols)):
+        busy = {r: -1 for r in seg}
+        for c in cols:
             part = [r for r in seg if P[r, c]]
+            lvl = 1 + max(busy[r] for r in part)
             u = np.zeros(N, bool)
             for r in part:
                 u |= P[r]
             for r in part:
                 P[r] |= u
-            need |= u
+                busy[r] = lvl
+            level_of_col[c] = lvl
+            groups.append((lvl, g, c, part, u.copy()))
+    n_levels = 1 + max(l for l, *_ in groups)
+    levels, first_shared = [], []
+    for T in range(n_levels):
+        here = [(g, c, part) for (l, g, c, part, u) in groups if l == T]
+        for g in range(len(segments)):            # groups of one segment on one level never share a row
+            rows = [r for (gg, c, part) in here if gg == g for r in part]
+            assert len(rows) == len(set(rows))
+        need = np.zeros(N, bool)
+        for (l, g, c, part, u) in groups:
+            if l == T:
+                need |= u
         shared = [c for c in range(K1, N) if need[c]]
-        first.append(min(shared) if shared else N)
-    return first
+        levels.append(here)
+        first_shared.append(min(shared) if shared else N)
+    return levels, level_of_col, first_shared
 
 
 def column_classes(hx_terms):
@@ -265,19 +282,40 @@ def build():
 
     # ---- block structure -> lane permutation and register slots -------------------------------------------
     K1, segments, seg_cols = analyze_blocks(hx_terms)
-    sp_first_shared = superstep_shared_columns(hx_terms, K1, segments, seg_cols)
+    levels, level_of_col, sp_first_shared = level_schedule(hx_terms, K1, segments, seg_cols)
     SEG = 6
     row_of_lane = [-1] * WARP
     for g, seg in enumerate(segments):
         for i, r in enumerate(seg):
             row_of_lane[g * SEG + i] = r
     lane_of_row = [row_of_lane.index(r) for r in range(N)]
-    nsp = max(len(c) for c in seg_cols)
+    nsp = len(levels)
     nd = N - K1
+    # per lane and level: the private column the lane's row meets there (or None), the lanes of its group (6-bit mask relative
+    # to the segment's first lane) and the group's index within the segment (selects the pivot-row buffer)
+    col_at = [[None] * nsp for _ in range(WARP)]
+    grp_mask = [[0] * nsp for _ in range(WARP)]
+    grp_sub = [[0] * nsp for _ in range(WARP)]
+    max_sub = 1
+    for T, here in enumerate(levels):
+        n_in_seg = {}
+        for (g, c, part) in here:
+            sub = n_in_seg.get(g, 0)
+            n_in_seg[g] = sub + 1
+            max_sub = max(max_sub, sub + 1)
+            mask = 0
+            for r in part:
+                mask |= 1 << (lane_of_row[r] - g * SEG)
+            for r in part:
+                ln = lane_of_row[r]
+                col_at[ln][T], grp_mask[ln][T], grp_sub[ln][T] = c, mask, sub
+    assert max_sub <= 2
 
     def slot_of(lane, col):
-        g = lane // SEG
-        return seg_cols[g].index(col) if col < K1 else nsp + (col - K1)
+        if col >= K1:
+            return nsp + (col - K1)
+        assert col_at[lane][level_of_col[col]] == col
+        return level_of_col[col]
 
     # ---- x-product table: [x(32 entries, x[30] = 1) | pairs (padded to a multiple of 32) | triples] -------------------
     pairs, triples = set(), set()
@@ -367,27 +405,26 @@ def build():
         tri_by_pos[xp_pos[XP_TRI0 + i] - XP_TRI0] = tr
 
     # ---- scatter of the class accumulators into register slots --------------------------------------------------
-    # slot t of a lane holds column seg_cols[g][t] (t < nsp) or K1 + (t - nsp); the class feeding it may depend on the
-    # segment -> at most two candidates per slot, chosen by one per-lane selector bit
+    # slot t of a lane holds the private column its row meets on level t (t < nsp) or K1 + (t - nsp); the class feeding it may
+    # depend on the lane -> at most two candidates per slot, chosen by one per-lane selector bit
     nslot = nsp + nd
     scatter = []           # per slot: (classA, classB or -1, selector bit index or -1)
     sel_of_lane = [0] * WARP
     nz_of_lane = [0] * WARP
     n_sel = 0
     for t in range(nslot):
-        cls_per_seg = []
-        for g in range(len(segments)):
-            col = (seg_cols[g][t] if t < len(seg_cols[g]) else None) if t < nsp else K1 + (t - nsp)
-            cls_per_seg.append(col_class.get(col) if col is not None else None)
-        used = sorted({c for c in cls_per_seg if c is not None})
+        cls_per_lane = []
+        for lane in range(WARP):
+            col = col_at[lane][t] if t < nsp else (K1 + (t - nsp) if row_of_lane[lane] >= 0 else None)
+            cls_per_lane.append(col_class.get(col) if col is not None else None)
+        used = sorted({c for c in cls_per_lane if c is not None})
         assert 1 <= len(used) <= 2
         if len(used) == 1:
             scatter.append((used[0], -1, -1))
         else:
             scatter.append((used[0], used[1], n_sel))
             for lane in range(WARP):
-                g = lane // SEG
-                if g < len(segments) and cls_per_seg[g] == used[1]:
+                if cls_per_lane[lane] == used[1]:
                     sel_of_lane[lane] |= 1 << n_sel
             n_sel += 1
     for lane in range(WARP):
@@ -400,7 +437,8 @@ def build():
     return dict(hx_terms=hx_terms, h_terms=h_terms, cq_list=cq_list, dq_list=dq_list, classes=classes,
                 col_class=col_class, hx_slots=hx_slots, h_slots=h_slots, ht_slots=ht_slots,
                 K1=K1, segments=segments, seg_cols=seg_cols, row_of_lane=row_of_lane, lane_of_row=lane_of_row,
-                nsp=nsp, nd=nd, nslot=nslot, sp_first_shared=sp_first_shared, scatter=scatter, sel_of_lane=sel_of_lane, nz_of_lane=nz_of_lane, n_sel=n_sel,
+                nsp=nsp, nd=nd, nslot=nslot, sp_first_shared=sp_first_shared, levels=levels, level_of_col=level_of_col,
+                col_at=col_at, grp_mask=grp_mask, grp_sub=grp_sub, max_sub=max_sub, scatter=scatter, sel_of_lane=sel_of_lane, nz_of_lane=nz_of_lane, n_sel=n_sel,
                 pairs=pair_by_pos, triples=tri_by_pos, XP_PAIR0=XP_PAIR0, XP_TRI0=XP_TRI0, XP_TOTAL=XP_TOTAL,
                 layout_cost=layout_cost)
 
@@ -495,8 +533,10 @@ def emit(g, path):
     # ---- block structure ----------------------------------------------------------------------------------------
     w("// block structure: %d segments of 6 lanes; sparse pivot columns per segment %s; dense columns %d..%d"
       % (len(g["segments"]), g["seg_cols"], g["K1"], N - 1))
+    for T, here in enumerate(g["levels"]):
+        w("//   level %d: %s" % (T, "  ".join("col %d rows %s" % (c, part) for (_, c, part) in here)))
     w("#define HCG_K1 %d        /* first dense pivot column */" % g["K1"])
-    w("#define HCG_NSP %d        /* sparse slots (super-steps) */" % g["nsp"])
+    w("#define HCG_NSP %d        /* sparse slots == levels (super-steps) */" % g["nsp"])
     w("#define HCG_ND %d        /* dense slots */" % g["nd"])
     w("#define HCG_NSLOT %d     /* register slots per row */" % g["nslot"])
     w("#define HCG_SEG 6")
@@ -505,20 +545,22 @@ def emit(g, path):
     w("#define HCG_SP_FIRST_SHARED_SLOT_INIT { " + ",".join(str(g["nsp"] + c - g["K1"]) for c in g["sp_first_shared"]) + " }")
     w("#define HCG_ROW_OF_LANE_INIT { " + ",".join(str(r) for r in g["row_of_lane"]) + " }")
     w("#define HCG_LANE_OF_ROW_INIT { " + ",".join(str(r) for r in g["lane_of_row"]) + " }")
-    # per-lane info word: nz mask over slots (bits 0..nslot-1) | selector bits << 20 | number of sparse columns << 24
-    info, cols = [], []
+    # per-lane info word: nz mask over slots (bits 0..nslot-1) | selector bits << 20
+    info, cols, grps = [], [], []
     for lane in range(WARP):
-        gseg = lane // 6
-        ns = len(g["seg_cols"][gseg]) if gseg < len(g["segments"]) and g["row_of_lane"][lane] >= 0 else 0
-        assert g["nslot"] <= 20 and g["n_sel"] <= 4
-        info.append(g["nz_of_lane"][lane] | (g["sel_of_lane"][lane] << 20) | (ns << 24))
-        packed = 0
-        if ns:
-            for t, c in enumerate(g["seg_cols"][gseg]):
-                packed |= c << (5 * t)
+        assert g["nslot"] <= 20 and g["n_sel"] <= 4 and g["nsp"] <= 4
+        info.append(g["nz_of_lane"][lane] | (g["sel_of_lane"][lane] << 20))
+        packed, gp = 0, 0
+        for t in range(g["nsp"]):
+            if g["col_at"][lane][t] is not None:
+                packed |= g["col_at"][lane][t] << (5 * t)
+                gp |= (g["grp_mask"][lane][t] | (g["grp_sub"][lane][t] << 6)) << (7 * t)
         cols.append(packed)
+        grps.append(gp)
     w("#define HCG_LANEINFO_INIT { " + ",".join("0x%08xu" % v for v in info) + " }")
-    w("#define HCG_LANECOLS_INIT { " + ",".join("0x%08xu" % v for v in cols) + " }   /* 5 bits per sparse slot: its matrix column */")
+    w("#define HCG_LANECOLS_INIT { " + ",".join("0x%08xu" % v for v in cols) + " }   /* 5 bits per level: the private column the lane's row meets there */")
+    w("#define HCG_LANEGRP_INIT { " + ",".join("0x%08xu" % v for v in grps) + " }   /* 7 bits per level: lanes of my pivot group (6, relative to the segment) | group index << 6; 0 = idle */")
+    w("#define HCG_MAX_GROUPS_PER_SEG %d" % g["max_sub"])
     w("// X(slot, class): one Hx term slot; acc[class] += cq * xprod")
     w("#define HCG_HX_SLOT_LIST(X) \\")
     for s, (ci, _) in enumerate(g["hx_slots"]):
