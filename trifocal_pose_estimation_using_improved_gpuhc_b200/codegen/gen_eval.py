@@ -562,6 +562,16 @@ def emit(g, path):
     w("#define HCG_LANEGRP_INIT { " + ",".join("0x%08xu" % v for v in grps) + " }   /* 7 bits per level: lanes of my pivot group (6, relative to the segment) | group index << 6; 0 = idle */")
     w("#define HCG_MAX_GROUPS_PER_SEG %d" % g["max_sub"])
     w("// X(slot, class): one Hx term slot; acc[class] += cq * xprod")
+    # slots are ordered by class: first slot of every class (+ end), for the rolled per-class loops of the evaluator
+    begs, prev = [], None
+    for i, (ci, _) in enumerate(g["hx_slots"]):
+        if ci != prev:
+            assert prev is None or ci == prev + 1
+            begs.append(i)
+            prev = ci
+    begs.append(len(g["hx_slots"]))
+    assert len(begs) == len(g["classes"]) + 1
+    w("#define HCG_HX_CLASS_BEGIN_INIT { " + ",".join(str(b) for b in begs) + " }   /* first Hx slot of every class, then the end */")
     w("#define HCG_HX_SLOT_LIST(X) \\")
     for s, (ci, _) in enumerate(g["hx_slots"]):
         w("  X(%d, %d) \\" % (s, ci))
