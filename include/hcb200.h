@@ -57,7 +57,8 @@ size_t hcb200_workspace_bytes(void);
 int hcb200_abi_version(void);
 
 /* Replaces kernel_GPUHC_trifocal_2op1p_30x30_PH_CodeOpt_TrunPaths (…TrunPaths.cu:292-386).
- * Tracks all 312*n_hyp paths in one launch.  `stats` may be NULL.  Returns a cudaError_t value (0 == success). */
+ * Tracks all 312*n_hyp paths in one launch (0 <= n_hyp <= 3 441 480: path ids are 31-bit).  `stats` may be NULL.
+ * Returns a cudaError_t value (0 == success; cudaErrorInvalidValue for NULL buffers or out-of-range counts, nothing launched). */
 int hcb200_track(void* stream, int n_hyp,
                  int hc_max_steps, int hc_max_correction_steps, int hc_delta_t_incremental_steps, unsigned flags,
                  const float* d_start_sols, const float* d_start_params,

@@ -88,6 +88,9 @@ def test_edge_cases_empty_and_invalid(problem):
     rc = lib.hcb200_track(None, -1, 80, 3, 4, 1, p(trk.d_start_sols), p(trk.d_start_params), p(trk.d_target), p(trk.d_diff),
                           p(trk.d_tracks), p(trk.d_conv), p(trk.d_inf), None, p(trk.d_ws))
     assert rc != 0
+    rc = lib.hcb200_track(None, 4_000_000, 80, 3, 4, 1, p(trk.d_start_sols), p(trk.d_start_params), p(trk.d_target), p(trk.d_diff),
+                          p(trk.d_tracks), p(trk.d_conv), p(trk.d_inf), None, p(trk.d_ws))
+    assert rc != 0                                    # more hypotheses than 31-bit path ids allow: refused, nothing launched
     assert lib.hcb200_error_string(rc)
 
 
