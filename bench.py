@@ -343,8 +343,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None,
-                         "traffic": 2034688, "traffic_source": "dram__bytes_read.sum (2.03 MB) + dram__bytes_write.sum (8 KB) of the tracker launch, "
-                                                              "ncu --set full capture v8 in profiles/ncu_r1.md (0.2-2 MB across captures); the 7.8 MB of results stay in the 126 MB L2",
+                         "traffic": 2267392, "traffic_source": "dram__bytes_read.sum (2.03 MB) + dram__bytes_write.sum (0.24 MB) of the tracker launch, "
+                                                              "ncu --set full capture v11 in profiles/ncu_r1.md (0.2-2 MB across captures); the 7.8 MB of results stay in the 126 MB L2",
                          "hbm": {"algorithmic_bytes_per_launch": H * (2 * 34 * 8) + n_paths * (31 * 8 + 2),
                                  "achieved_gbs": (H * (2 * 34 * 8) + n_paths * (31 * 8 + 2)) / (ms_per_step * 1e-3) / 1e9,
                                  "peak_gbs": 6553.0, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
