@@ -348,3 +348,32 @@ def test_device_scoring_matches_host_evaluations(problem, ransac0, default_round
     assert n_cand >= 5
     assert best[0] == 1 and best[1] == best_path == 104 and best[4] == n_cand
     assert (best[2], best[3]) == (5117, 5117)
+
+
+def test_launch_is_stream_ordered_and_graph_capturable(problem, default_round):
+    """The C ABI only ENQUEUES (workspace reset + one kernel) on the caller's stream — no synchronisation, no allocation — so a round
+    can be captured in a CUDA graph and replayed; the replay gives the same bits as a direct launch."""
+    import torch
+    picked, target, diff = default_round
+    H = 8
+    trk = hc.Tracker(problem=problem)
+    trk.upload_params(target[:H], diff[:H])
+    trk.track(H, prune=True)
+    tr0, cv0, inf0, _ = trk.results(H)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        trk.track(H, prune=True)                       # warm-up on the capture stream (function attributes are set here)
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            trk.track(H, prune=True)
+    for _ in range(2):
+        trk.d_tracks.zero_(); trk.d_conv.zero_(); trk.d_inf.zero_()
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
+        tr1, cv1, inf1, _ = trk.results(H)
+        assert np.array_equal(cv0, cv1) and np.array_equal(inf0, inf1)
+        assert np.array_equal(np.ascontiguousarray(tr0).view(np.uint64), np.ascontiguousarray(tr1).view(np.uint64)) or \
+            bool(np.all((np.ascontiguousarray(tr0).view(np.uint64) == np.ascontiguousarray(tr1).view(np.uint64)) | np.isnan(tr0) & np.isnan(tr1)))
