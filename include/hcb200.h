@@ -34,7 +34,7 @@ extern "C" {
 #define HCB200_NUM_VARS 30
 #define HCB200_NUM_PARAMS 33
 #define HCB200_NUM_TRACKS 312
-#define HCB200_ABI_VERSION 1
+#define HCB200_ABI_VERSION 2
 
 /* flags */
 #define HCB200_FLAG_PRUNE_PATHS 1u   /* positive-depth path pruning (always on in the reference GPU kernels, …TrunPaths.cu:148-154) */
@@ -51,6 +51,19 @@ typedef struct {
   int32_t n_passed;         /* number of paths that passed before the launch drained                   */
   int32_t reserved[11];
 } hcb200_best_record;
+
+/* What one GPU contributes to the multi-GPU result exchange (128 bytes): its best candidate with the pose, and its early-abort
+ * flag.  Replaces the host-side stacking of every GPU's tracks (GPU_HC_Solver.cpp:449-506) when only the selected pose is needed
+ * (BASELINE.json north_star (4): "only a tiny gather of each GPU's best pose and early-abort flag"). */
+typedef struct {
+  int32_t found;            /* this GPU has a pose candidate (score launch) / a passing path (abort launch)      */
+  int32_t inliers21, inliers31;
+  int32_t n_candidates;     /* candidates (score) or passing paths (abort) on this GPU; summed by the reduction   */
+  int32_t abort_flag;       /* the GPU's early-abort flag; OR-ed by the reduction                                 */
+  int32_t rank;             /* GPU / rank that owns the winning record                                            */
+  long long path_id;        /* GLOBAL path id (hypothesis * 312 + track over the whole round), -1 when none       */
+  float pose[24];           /* R21 row-major [9], t21 [3] (unit length), R31 [9], t31 [3] of that path            */
+} hcb200_pose_record;
 
 /* Device workspace the launches need (work counter + reduction scratch); zeroing is done by the launch itself. */
 size_t hcb200_workspace_bytes(void);
@@ -101,6 +114,14 @@ int hcb200_build_target_params(void* stream, int n_hyp, const int32_t* d_picked,
 int hcb200_score_tracks(void* stream, int n_paths, const float* d_tracks, const uint8_t* d_converged, int n_edgels,
                         const float* d_edgel_locations, const float* d_intrinsic, int32_t* d_support,
                         hcb200_best_record* d_best, void* d_workspace);
+
+/* Multi-GPU result exchange, device side.  hcb200_make_pose_record turns the best record of the last score / abort launch on
+ * this GPU into the 128-byte exchange record (pose from the track's Cayley parameters, host/mvg.hpp arithmetic; path_offset =
+ * 312 * first hypothesis of this GPU's shard; d_found may be NULL).  hcb200_reduce_pose_records reduces n <= 32 gathered records
+ * to the round's result: largest min(inliers21, inliers31), lowest global path id among equals. */
+int hcb200_make_pose_record(void* stream, const float* d_tracks, const hcb200_best_record* d_best, const uint8_t* d_found,
+                            long long path_offset, int rank, hcb200_pose_record* d_out);
+int hcb200_reduce_pose_records(void* stream, int n_records, const hcb200_pose_record* d_records, hcb200_pose_record* d_out);
 
 /* Newton refinement of converged end points on the device (next row of SURVEY.md §8f-3; the reference has no such kernel — it is
  * what Evaluations::Find_Unique_Sols, reference Evaluations.cpp:184-233, needs before end points can be compared at

@@ -248,11 +248,220 @@ static float butterfly_sum(const float* v30)
 }
 
 /* ------------------------------------------------------------------------------------------------------------
- * one path: …TrunPaths.cu:80-286 (SURVEY.md App. B), cfg->prune == 0 gives CPUHC_Generic_Solver_Eval_by_Indx.cpp:67-172 */
-void hco_track_path(const int* dHdx, const int* dHdt, const hco_c32* start_sol31, const hco_c32* sp,
-                    const hco_c32* tp, const hco_c32* dp, const hco_settings* cfg,
-                    hco_c32* out_track31, uint8_t* out_conv, uint8_t* out_inf, hco_path_stats* st)
+ * ARITHMETIC VARIANTS (hco_variant, hc_oracle.h) — equally valid floating-point evaluations of the SAME algorithm, used only to
+ * measure how far rounding alone moves the integer results (tools/parity_envelope.py, tests/test_parity_envelope.py).  Variant 0
+ * everywhere is the spec above; the others restate what the reference's own two implementations do at that point. */
+static inline hco_c32 c_mul_v(hco_c32 a, hco_c32 b, int contract)      /* MAGMA operator*: (ar*br - ai*bi, ai*br + ar*bi) */
 {
+  if (contract) return c_make(fmaf(a.re, b.re, -(a.im * b.im)), fmaf(a.im, b.re, a.re * b.im));   /* nvcc / gcc -ffp-contract=fast */
+  return c_make(a.re * b.re - a.im * b.im, a.im * b.re + a.re * b.im);
+}
+/* term = coef * p[a] * p[b] * x[d] * x[e] (* x[f]) multiplied LEFT TO RIGHT, padded factors (== 1+0i) included, exactly as
+ * cpu-eval-indx_trifocal_2op1p_30x30.hpp:22-89 / …L2Cache.cuh:57-148 do (the integer coefficient enters as a real scale) */
+static void eval_Hx_ltr(const int* dHdx, const hco_c32* x, const hco_c32* p, hco_c32* A, int contract)
+{
+  for (int row = 0; row < HCO_N; row++)
+    for (int col = 0; col < HCO_N; col++) {
+      hco_c32 acc = c_make(0.0f, 0.0f);
+      for (int j = 0; j < HCO_HX_TERMS; j++) {
+        const int base = (col * HCO_HX_TERMS * HCO_HX_PARTS + j * HCO_HX_PARTS) * HCO_N + row;
+        hco_c32 t = c_scale((float)dHdx[base], p[dHdx[base + 1 * HCO_N]]);
+        t = c_mul_v(t, p[dHdx[base + 2 * HCO_N]], contract);
+        t = c_mul_v(t, x[dHdx[base + 3 * HCO_N]], contract);
+        t = c_mul_v(t, x[dHdx[base + 4 * HCO_N]], contract);
+        acc = c_add(acc, t);
+      }
+      A[row * HCO_N + col] = acc;
+    }
+}
+static void eval_H_ltr(const int* dHdt, const hco_c32* x, const hco_c32* p, hco_c32* b, int contract)
+{
+  for (int row = 0; row < HCO_N; row++) {
+    hco_c32 acc = c_make(0.0f, 0.0f);
+    for (int j = 0; j < HCO_HT_TERMS; j++) {
+      const int base = (j * HCO_HT_PARTS) * HCO_N + row;
+      hco_c32 t = c_scale((float)dHdt[base], p[dHdt[base + 1 * HCO_N]]);
+      t = c_mul_v(t, p[dHdt[base + 2 * HCO_N]], contract);
+      t = c_mul_v(t, x[dHdt[base + 3 * HCO_N]], contract);
+      t = c_mul_v(t, x[dHdt[base + 4 * HCO_N]], contract);
+      t = c_mul_v(t, x[dHdt[base + 5 * HCO_N]], contract);
+      acc = c_add(acc, t);
+    }
+    b[row] = acc;
+  }
+}
+static void eval_Ht_ltr(const int* dHdt, const hco_c32* x, const hco_c32* p, const hco_c32* dp, hco_c32* b, int contract)
+{
+  for (int row = 0; row < HCO_N; row++) {
+    hco_c32 acc = c_make(0.0f, 0.0f);
+    for (int j = 0; j < HCO_HT_TERMS; j++) {
+      const int base = (j * HCO_HT_PARTS) * HCO_N + row;
+      const int ia = dHdt[base + 1 * HCO_N], ib = dHdt[base + 2 * HCO_N];
+      /* …L2Cache.cuh:110-116: coef * (dp[a]*p[b] + dp[b]*p[a]) * x * x * x */
+      hco_c32 t = c_scale((float)dHdt[base], c_add(c_mul_v(dp[ia], p[ib], contract), c_mul_v(dp[ib], p[ia], contract)));
+      t = c_mul_v(t, x[dHdt[base + 3 * HCO_N]], contract);
+      t = c_mul_v(t, x[dHdt[base + 4 * HCO_N]], contract);
+      t = c_mul_v(t, x[dHdt[base + 5 * HCO_N]], contract);
+      acc = c_sub(acc, t);
+    }
+    b[row] = acc;
+  }
+}
+
+/* the spec's elimination with the reference's pivot rule (exact |re|+|im| maximum, first one in row order wins) and/or the
+ * reference's division (cuCdivf scaling) for 1/pivot */
+static int solve_gj_variant(hco_c32* A, hco_c32* b, int exact_key, int cudiv_recip)
+{
+  int done[HCO_N], piv[HCO_N];
+  hco_c32 rsave[HCO_N];
+  for (int i = 0; i < HCO_N; i++) done[i] = 0;
+  for (int k = 0; k < HCO_N; k++) {
+    int p = -1;
+    if (exact_key) {
+      float best = -1.0f;
+      for (int i = 0; i < HCO_N; i++) {
+        if (done[i]) continue;
+        float v = fabsf(A[i * HCO_N + k].re) + fabsf(A[i * HCO_N + k].im);
+        if (v != v) v = INFINITY;
+        if (v > best) { best = v; p = i; }
+      }
+      if (!(best > 0.0f)) { for (int i = 0; i < HCO_N; i++) b[i] = c_make(NAN, NAN); return k + 1; }
+    } else {
+      uint32_t maxkey = 0;
+      for (int i = 0; i < HCO_N; i++) {
+        if (done[i]) continue;
+        const uint32_t key = (key_bits(fabsf(A[i * HCO_N + k].re) + fabsf(A[i * HCO_N + k].im)) & ~31u) | (uint32_t)(31 - i);
+        if (key > maxkey) { maxkey = key; p = i; }
+      }
+      if (maxkey < 32u) { for (int i = 0; i < HCO_N; i++) b[i] = c_make(NAN, NAN); return k + 1; }
+    }
+    done[p] = 1; piv[k] = p;
+    const hco_c32 r = cudiv_recip ? c_div_cu(c_make(1.0f, 0.0f), A[p * HCO_N + k]) : c_recip(A[p * HCO_N + k]);
+    rsave[p] = r;
+    for (int i = 0; i < HCO_N; i++) {
+      if (i == p) continue;
+      if (A[i * HCO_N + k].re == 0.0f && A[i * HCO_N + k].im == 0.0f) continue;
+      const hco_c32 m = c_mul(A[i * HCO_N + k], r);
+      for (int j = k + 1; j < HCO_N; j++) A[i * HCO_N + j] = c_msub(A[i * HCO_N + j], m, A[p * HCO_N + j]);
+      b[i] = c_msub(b[i], m, b[p]);
+    }
+  }
+  hco_c32 x[HCO_N];
+  for (int k = 0; k < HCO_N; k++) x[k] = c_mul(b[piv[k]], rsave[piv[k]]);
+  memcpy(b, x, sizeof x);
+  return 0;
+}
+
+/* literal reference LU (hco_solve_lu_ref) with the multiply-adds contracted the way nvcc -O3 (fmad on) compiles
+ * dev-cgesv-batched-small.cuh:84-106: a - m*u  ->  re = fma(-m.re,u.re, fma(m.im,u.im,a.re)) … */
+static inline hco_c32 c_msub_contract(hco_c32 a, hco_c32 m, hco_c32 u)
+{
+  const hco_c32 t = c_make(fmaf(m.re, u.re, -(m.im * u.im)), fmaf(m.im, u.re, m.re * u.im));
+  return c_make(a.re - t.re, a.im - t.im);
+}
+static int solve_lu_ref_contract(hco_c32* A, hco_c32* b)
+{
+  int rowid[HCO_N], info = 0;
+  hco_c32 sx[HCO_N], sB[HCO_N];
+  float dsx[HCO_N];
+  for (int i = 0; i < HCO_N; i++) rowid[i] = i;
+  for (int i = 0; i < HCO_N; i++) {
+    for (int t = 0; t < HCO_N; t++) dsx[rowid[t]] = fabsf(A[t * HCO_N + i].re) + fabsf(A[t * HCO_N + i].im);
+    float mx = dsx[i]; int max_id = i;
+    for (int j = i + 1; j < HCO_N; j++) if (dsx[j] > mx) { max_id = j; mx = dsx[j]; }
+    int zero = (mx == 0.0f);
+    if (zero && !info) info = i + 1;
+    float update = zero ? 0.0f : 1.0f;
+    hco_c32 sB0 = c_make(0, 0);
+    for (int t = 0; t < HCO_N; t++) {
+      if (rowid[t] == max_id) {
+        rowid[t] = i;
+        for (int j = i; j < HCO_N; j++) sx[j] = c_scale(update, A[t * HCO_N + j]);
+        sB0 = b[t];
+      } else if (rowid[t] == i) rowid[t] = max_id;
+    }
+    hco_c32 reg = zero ? c_make(1, 0) : c_div_cu(c_make(1, 0), sx[i]);
+    for (int t = 0; t < HCO_N; t++) {
+      if (rowid[t] > i) {
+        A[t * HCO_N + i] = c_mul_v(A[t * HCO_N + i], reg, 1);
+        for (int j = i + 1; j < HCO_N; j++) A[t * HCO_N + j] = c_msub_contract(A[t * HCO_N + j], A[t * HCO_N + i], sx[j]);
+        b[t] = c_msub_contract(b[t], A[t * HCO_N + i], sB0);
+      }
+    }
+  }
+  for (int t = 0; t < HCO_N; t++) sB[rowid[t]] = b[t];
+  for (int i = HCO_N - 1; i >= 0; i--) {
+    for (int t = 0; t < HCO_N; t++) sx[rowid[t]] = A[t * HCO_N + i];
+    hco_c32 reg = c_div_cu(sB[i], sx[i]);
+    for (int t = 0; t < i; t++) sB[t] = c_msub_contract(sB[t], reg, sx[t]);
+    sB[i] = reg;
+  }
+  memcpy(b, sB, sizeof sB);
+  return info;
+}
+
+static void solve_variant(const hco_variant* v, hco_c32* A, hco_c32* b)
+{
+  switch (v ? v->solver : 0) {
+    case 1: hco_solve_lu_ref(A, b); break;
+    case 2: solve_lu_ref_contract(A, b); break;
+    case 3: solve_gj_variant(A, b, 1, 0); break;
+    case 4: solve_gj_variant(A, b, 0, 1); break;
+    case 5: solve_gj_variant(A, b, 1, 1); break;
+    default: hco_solve(A, b);
+  }
+}
+
+/* norm sums.  0: the spec's xor butterfly (== the reference GPU's shuffle-down tree as lane 0 sees it when the two lanes that
+ * do not exist contribute 0); 1: sequential i = 0..29 (reference CPU-HC, CPUHC_make_correction); 2: the reference GPU's
+ * shuffle-down tree when a shuffle from a lane that does not exist returns the CALLER's own value (lanes 14 and 15 count twice
+ * at offset 16, …TrunPaths.cu:236-239; which of 0 / 2 the hardware does is measured by tools/probes.cu) */
+static float sum_variant(const hco_variant* v, const float* v30)
+{
+  const int mode = v ? v->sum_order : 0;
+  if (mode == 1) { float s = 0.0f; for (int i = 0; i < HCO_N; i++) s += v30[i]; return s; }
+  if (mode == 2) {
+    float a[32];
+    for (int i = 0; i < 32; i++) a[i] = i < HCO_N ? v30[i] : 0.0f;
+    for (int off = 16; off > 0; off >>= 1) {
+      float w[32];
+      for (int i = 0; i < HCO_N; i++) { const int src = i + off; w[i] = a[i] + ((src < HCO_N) ? a[src] : a[i]); }
+      for (int i = 0; i < HCO_N; i++) a[i] = w[i];
+    }
+    return a[0];
+  }
+  return butterfly_sum(v30);
+}
+
+/* stochastic-arithmetic variants: every component of every solve result is moved by -1 / 0 / +1 ulp, pseudo-randomly but
+ * reproducibly (counter-based hash of seed, path, solve number, component).  A perturbation of one unit in the last place of
+ * the linear-solve result is far below the solve's own backward error, so each seed is another legitimate rounding of the path. */
+static inline uint32_t mix32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
+static inline float ulp_nudge(float f, uint32_t r)
+{
+  if (!(f == f) || isinf(f) || f == 0.0f) return f;
+  const uint32_t k = r % 3u;           /* 0: keep, 1: up, 2: down */
+  if (k == 0) return f;
+  return nextafterf(f, k == 1 ? INFINITY : -INFINITY);
+}
+static void perturb_solution(const hco_variant* v, uint32_t path_key, uint32_t solve_no, hco_c32* b)
+{
+  if (!v || !v->perturb_seed) return;
+  for (int i = 0; i < HCO_N; i++) {
+    const uint32_t r = mix32(v->perturb_seed * 0x9e3779b9u ^ mix32(path_key * 0x85ebca6bu ^ mix32(solve_no * 64u + (uint32_t)i)));
+    b[i].re = ulp_nudge(b[i].re, r);
+    b[i].im = ulp_nudge(b[i].im, r >> 8);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * one path: …TrunPaths.cu:80-286 (SURVEY.md App. B), cfg->prune == 0 gives CPUHC_Generic_Solver_Eval_by_Indx.cpp:67-172 */
+void hco_track_path_v(const int* dHdx, const int* dHdt, const hco_c32* start_sol31, const hco_c32* sp,
+                      const hco_c32* tp, const hco_c32* dp, const hco_settings* cfg, const hco_variant* v, uint32_t path_key,
+                      hco_c32* out_track31, uint8_t* out_conv, uint8_t* out_inf, hco_path_stats* st)
+{
+  const int ltr = v ? v->term_order : 0, contract = v ? v->contract : 0;
+  uint32_t solve_no = 0;
   hco_c32 x[HCO_N + 1], last[HCO_N], sols[HCO_N], p[HCO_NP + 1], A[HCO_N * HCO_N], b[HCO_N];
   for (int i = 0; i < HCO_N; i++) x[i] = last[i] = sols[i] = start_sol31[i];
   x[HCO_N] = c_make(1.0f, 0.0f);
@@ -281,9 +490,10 @@ void hco_track_path(const int* dHdx, const int* dHdt, const hco_c32* start_sol31
     /* RK4 predictor, "loopy" form (:170-211) */
     for (int r = 0; r < 4; r++) {
       hco_param_homotopy(t0, sp, tp, p);
-      hco_eval_Hx(dHdx, x, p, A);
-      hco_eval_Ht(dHdt, x, p, dp, b);
-      hco_solve(A, b);
+      if (ltr) { eval_Hx_ltr(dHdx, x, p, A, contract); eval_Ht_ltr(dHdt, x, p, dp, b, contract); }
+      else { hco_eval_Hx(dHdx, x, p, A); hco_eval_Ht(dHdt, x, p, dp, b); }
+      solve_variant(v, A, b);
+      perturb_solution(v, path_key, solve_no++, b);
       s.pred_stages++;
       if (r < 3) {
         const float sc = (r < 2) ? half : delta_t;
@@ -294,10 +504,16 @@ void hco_track_path(const int* dHdx, const int* dHdt, const hco_c32* start_sol31
           x[i].im = fmaf(b[i].im, sc, last[i].im);
         }
         if (r != 1) t0 += half;
-      } else {
+      } else if (v && v->rk_final_mul) {                  /* variant: multiply by (float)(1/6) like the first three stages */
         for (int i = 0; i < HCO_N; i++) {
           sols[i].re = fmaf(b[i].re * delta_t, c6[0], sols[i].re);
           sols[i].im = fmaf(b[i].im * delta_t, c6[0], sols[i].im);
+          x[i] = sols[i];
+        }
+      } else {                                            /* :209  s_sols += sB * delta_t * 1.0/6.0  ==  (sB*delta_t) / 6.0f, IEEE division */
+        for (int i = 0; i < HCO_N; i++) {
+          sols[i].re = sols[i].re + (b[i].re * delta_t) / 6.0f;
+          sols[i].im = sols[i].im + (b[i].im * delta_t) / 6.0f;
           x[i] = sols[i];
         }
       }
@@ -305,9 +521,10 @@ void hco_track_path(const int* dHdx, const int* dHdt, const hco_c32* start_sol31
 
     /* Newton corrector (:216-250); the parameter homotopy is NOT re-evaluated */
     for (int c = 0; c < cfg->max_corr_steps; c++) {
-      hco_eval_Hx(dHdx, x, p, A);
-      hco_eval_H(dHdt, x, p, b);
-      hco_solve(A, b);
+      if (ltr) { eval_Hx_ltr(dHdx, x, p, A, contract); eval_H_ltr(dHdt, x, p, b, contract); }
+      else { hco_eval_Hx(dHdx, x, p, A); hco_eval_H(dHdt, x, p, b); }
+      solve_variant(v, A, b);
+      perturb_solution(v, path_key, solve_no++, b);
       s.corr_stages++;
       float vd[HCO_N], vx[HCO_N];
       for (int i = 0; i < HCO_N; i++) {
@@ -315,7 +532,7 @@ void hco_track_path(const int* dHdx, const int* dHdt, const hco_c32* start_sol31
         vd[i] = fmaf(b[i].re, b[i].re, b[i].im * b[i].im);
         vx[i] = fmaf(x[i].re, x[i].re, x[i].im * x[i].im);
       }
-      const float sum_d = butterfly_sum(vd), sum_x = butterfly_sum(vx);
+      const float sum_d = sum_variant(v, vd), sum_x = sum_variant(v, vx);
       ok = (double)sum_d < 0.000001 * (double)sum_x;
       inf_fail = (double)sum_x > 1e14;
       if (inf_fail) break;
@@ -343,9 +560,19 @@ void hco_track_path(const int* dHdx, const int* dHdt, const hco_c32* start_sol31
   if (st) *st = s;
 }
 
+void hco_track_path(const int* dHdx, const int* dHdt, const hco_c32* start_sol31, const hco_c32* sp,
+                    const hco_c32* tp, const hco_c32* dp, const hco_settings* cfg,
+                    hco_c32* out_track31, uint8_t* out_conv, uint8_t* out_inf, hco_path_stats* st)
+{ hco_track_path_v(dHdx, dHdt, start_sol31, sp, tp, dp, cfg, NULL, 0u, out_track31, out_conv, out_inf, st); }
+
 void hco_track_batch(const int* dHdx, const int* dHdt, const hco_c32* start_sols, const hco_c32* sp,
                      const hco_c32* target, const hco_c32* diff, int n_hyp, const hco_settings* cfg, int n_threads,
                      hco_c32* tracks, uint8_t* converged, uint8_t* infinity, hco_path_stats* stats)
+{ hco_track_batch_v(dHdx, dHdt, start_sols, sp, target, diff, n_hyp, cfg, NULL, n_threads, tracks, converged, infinity, stats); }
+
+void hco_track_batch_v(const int* dHdx, const int* dHdt, const hco_c32* start_sols, const hco_c32* sp,
+                       const hco_c32* target, const hco_c32* diff, int n_hyp, const hco_settings* cfg, const hco_variant* v, int n_threads,
+                       hco_c32* tracks, uint8_t* converged, uint8_t* infinity, hco_path_stats* stats)
 {
   const long n_paths = (long)n_hyp * HCO_TRACKS;
 #ifdef _OPENMP
@@ -354,9 +581,9 @@ void hco_track_batch(const int* dHdx, const int* dHdt, const hco_c32* start_sols
   #pragma omp parallel for schedule(dynamic, 4)
   for (long ix = 0; ix < n_paths; ix++) {
     const int h = (int)(ix / HCO_TRACKS), s = (int)(ix % HCO_TRACKS);
-    hco_track_path(dHdx, dHdt, start_sols + (size_t)s * (HCO_N + 1), sp, target + (size_t)h * (HCO_NP + 1),
-                   diff + (size_t)h * (HCO_NP + 1), cfg, tracks + (size_t)ix * (HCO_N + 1), converged + ix, infinity + ix,
-                   stats ? stats + ix : NULL);
+    hco_track_path_v(dHdx, dHdt, start_sols + (size_t)s * (HCO_N + 1), sp, target + (size_t)h * (HCO_NP + 1),
+                     diff + (size_t)h * (HCO_NP + 1), cfg, v, (uint32_t)ix, tracks + (size_t)ix * (HCO_N + 1), converged + ix, infinity + ix,
+                     stats ? stats + ix : NULL);
   }
 }
 

@@ -46,6 +46,20 @@ typedef struct {          /* per-path counters (for the flop model of SURVEY.md 
   int32_t steps, pred_stages, corr_stages, rejected, end_reason; /* end_reason: 0 conv, 1 inf, 2 pruned, 3 step cap */
 } hco_path_stats;
 
+/* Arithmetic variant of the tracker (all zeros == the spec).  Every variant is the same algorithm with a different, equally
+ * valid floating-point evaluation at one point — what the reference's own CPU and GPU implementations do there.  Used only by
+ * the per-path parity analysis (tools/parity_envelope.py): a path whose flags differ between any two variants is UNSTABLE. */
+typedef struct {
+  int solver;         /* 0 spec; 1 literal reference LU + back substitution (dev-cgesv-batched-small.cuh:38-107), no contraction;
+                         2 the same with nvcc-style FMA contraction; 3 spec with the reference's exact-maximum pivot rule;
+                         4 spec with cuCdivf reciprocal; 5 spec with both */
+  int term_order;     /* 0 spec: (coef*p*p) * (x*x*x); 1 left to right as the reference evaluators multiply */
+  int contract;       /* with term_order 1: complex products with (1) / without (0) FMA contraction */
+  int sum_order;      /* 0 xor butterfly; 1 sequential (reference CPU); 2 reference GPU shuffle-down tree with own-value reads */
+  int rk_final_mul;   /* 1: last RK stage multiplies by (float)(1/6) (round-1 spec) instead of dividing by 6.0f (reference) */
+  unsigned perturb_seed; /* != 0: every solve result moved by -1/0/+1 ulp pseudo-randomly (stochastic arithmetic) */
+} hco_variant;
+
 /* evaluators: x31[30] and p34[33] must hold 1+0i; dHdx has 36000 ints, dHdt 2880 (reference token order) */
 void hco_eval_Hx(const int* dHdx, const hco_c32* x31, const hco_c32* p34, hco_c32* A_rowmajor);
 void hco_eval_Ht(const int* dHdt, const hco_c32* x31, const hco_c32* p34, const hco_c32* dp34, hco_c32* b30);
@@ -66,6 +80,14 @@ void hco_track_batch(const int* dHdx, const int* dHdt, const hco_c32* start_sols
                      const hco_c32* start_params34, const hco_c32* target /*[n_hyp][34]*/, const hco_c32* diff,
                      int n_hyp, const hco_settings* cfg, int n_threads,
                      hco_c32* tracks, uint8_t* converged, uint8_t* infinity, hco_path_stats* stats);
+
+/* the same under an arithmetic variant (NULL == spec); path_key seeds the perturbation stream of this path */
+void hco_track_path_v(const int* dHdx, const int* dHdt, const hco_c32* start_sol31, const hco_c32* start_params34,
+                      const hco_c32* target34, const hco_c32* diff34, const hco_settings* cfg, const hco_variant* v, uint32_t path_key,
+                      hco_c32* out_track31, uint8_t* out_converged, uint8_t* out_infinity, hco_path_stats* out_stats);
+void hco_track_batch_v(const int* dHdx, const int* dHdt, const hco_c32* start_sols, const hco_c32* start_params34,
+                       const hco_c32* target, const hco_c32* diff, int n_hyp, const hco_settings* cfg, const hco_variant* v, int n_threads,
+                       hco_c32* tracks, uint8_t* converged, uint8_t* infinity, hco_path_stats* stats);
 
 /* early-abort scoring of one end point: returns 1 if the solution passes (>= 90 % inliers in both view pairs);
  * n21/n31 receive the inlier counts (0 when the imaginary-part gate fails, gate_out tells). */

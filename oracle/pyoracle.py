@@ -14,6 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle_hc.so")
 REF_CPU_SO = os.path.join(HERE, "_ref", "libref_cpuhc.so")
+REF_CPU_PRUNED_SO = os.path.join(HERE, "_ref", "libref_cpuhc_pruned.so")   # reference CPU-HC + the GPU kernels' path pruning (generated copy)
 REF_GPU_SO = os.path.join(HERE, "_ref", "libref_gpuhc.so")
 
 N, NP1, TRACKS = 30, 34, 312
@@ -36,6 +37,12 @@ def f2c(a):
 class Settings(ctypes.Structure):
     _fields_ = [("max_steps", ctypes.c_int), ("max_corr_steps", ctypes.c_int), ("dt_inc_steps", ctypes.c_int),
                 ("prune", ctypes.c_int)]
+
+
+class Variant(ctypes.Structure):
+    """hco_variant (hc_oracle.h): an equally valid floating-point evaluation of the same algorithm; all zeros == the spec."""
+    _fields_ = [("solver", ctypes.c_int), ("term_order", ctypes.c_int), ("contract", ctypes.c_int), ("sum_order", ctypes.c_int),
+                ("rk_final_mul", ctypes.c_int), ("perturb_seed", ctypes.c_uint)]
 
 
 def build_oracle(force=False):
@@ -97,8 +104,9 @@ class Oracle:
                                            _vp(tgt), _vp(dif), _vp(picked))
         return f2c(tgt), f2c(dif), picked
 
-    def track(self, target, diff, prune, max_steps=80, max_corr=3, dt_inc=4, n_threads=0):
-        """Returns tracks[P,31] c64, converged[P] u8, infinity[P] u8, stats[P,5] i32 (steps,pred,corr,rejected,reason)."""
+    def track(self, target, diff, prune, max_steps=80, max_corr=3, dt_inc=4, n_threads=0, variant=None):
+        """Returns tracks[P,31] c64, converged[P] u8, infinity[P] u8, stats[P,5] i32 (steps,pred,corr,rejected,reason).
+        variant: dict of hco_variant fields (None == the arithmetic spec)."""
         n_hyp = target.shape[0]
         P = n_hyp * TRACKS
         tr = np.zeros((P, N + 1, 2), np.float32)
@@ -106,8 +114,9 @@ class Oracle:
         inf = np.zeros(P, np.uint8)
         st = np.zeros((P, 5), np.int32)
         cfg = Settings(max_steps, max_corr, dt_inc, 1 if prune else 0)
-        self.lib.hco_track_batch(_vp(self.hx), _vp(self.ht), _vp(self._ss), _vp(self._sp), _vp(c2f(target)), _vp(c2f(diff)),
-                                 n_hyp, ctypes.byref(cfg), n_threads or (os.cpu_count() or 1), _vp(tr), _vp(cv), _vp(inf), _vp(st))
+        var = ctypes.byref(Variant(**variant)) if variant else None
+        self.lib.hco_track_batch_v(_vp(self.hx), _vp(self.ht), _vp(self._ss), _vp(self._sp), _vp(c2f(target)), _vp(c2f(diff)),
+                                   n_hyp, ctypes.byref(cfg), var, n_threads or (os.cpu_count() or 1), _vp(tr), _vp(cv), _vp(inf), _vp(st))
         return f2c(tr), cv, inf, st
 
     def score(self, x31, locations, K):
@@ -134,11 +143,12 @@ class Oracle:
 class ReferenceCPU:
     """The real reference CPU-HC (oracle/_ref/libref_cpuhc.so)."""
 
-    def __init__(self):
-        if not os.path.exists(REF_CPU_SO):
-            raise FileNotFoundError(REF_CPU_SO + " (run `make -C oracle ref` in the build container)")
+    def __init__(self, pruned=False):
+        so = REF_CPU_PRUNED_SO if pruned else REF_CPU_SO
+        if not os.path.exists(so):
+            raise FileNotFoundError(so + " (run `make -C oracle ref` in the build container)")
         os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-        self.lib = ctypes.CDLL(REF_CPU_SO)
+        self.lib = ctypes.CDLL(so)
 
     def run(self, bin_dir, n_hyp, seed=0, dataset_index=0, n_cores=None, target=None):
         P = n_hyp * TRACKS

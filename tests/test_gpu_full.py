@@ -102,56 +102,7 @@ def tree(tmp_path_factory):
     return root
 
 
-class HostSolver:
-    def __init__(self, tree, overrides):
-        self.lib = ctypes.CDLL(os.path.join(LIBDIR, "libhcb200_host.so"))
-        self.lib.hcb200_solver_create.restype = ctypes.c_void_p
-        self.lib.hcb200_solver_kernel_seconds.restype = ctypes.c_double
-        for n in ("destroy", "allocate", "read_problem", "read_ransac", "prepare", "set_abort_arrays", "h2d", "solve", "free_round",
-                  "num_hypotheses", "kernel_seconds", "totals", "per_hypothesis", "copy_results", "copy_target_params", "best", "set_pruning"):
-            getattr(self.lib, "hcb200_solver_" + n).argtypes = [ctypes.c_void_p] + ([ctypes.c_void_p] * 3 if n in ("copy_results", "best") else
-                                                                              [ctypes.c_void_p] if n in ("totals", "per_hypothesis", "copy_target_params") else
-                                                                              [ctypes.c_int] if n in ("read_ransac", "set_pruning") else
-                                                                              [ctypes.c_uint] if n == "prepare" else [])
-        yaml = os.path.join(tree, "problems", "trifocal_2op1p_30x30", "gpuhc_settings.yaml")
-        ov = "Repo_Root=%s/;Verbose=false;%s" % (tree, overrides)
-        self.h = self.lib.hcb200_solver_create(yaml.encode(), ov.encode())
-        assert self.h
-
-    def round(self, dataset=0, seed=0, prune=True):
-        L, h = self.lib, self.h
-        assert L.hcb200_solver_allocate(h) == 0
-        assert L.hcb200_solver_read_problem(h) == 0 and L.hcb200_solver_read_ransac(h, dataset) == 0
-        L.hcb200_solver_set_pruning(h, 1 if prune else 0)
-        L.hcb200_solver_prepare(h, seed)
-        L.hcb200_solver_set_abort_arrays(h)
-        L.hcb200_solver_h2d(h)
-        L.hcb200_solver_solve(h)
-        H = L.hcb200_solver_num_hypotheses(h)
-        n = H * 312
-        tr = np.zeros((n, 31, 2), np.float32)
-        cv, inf = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
-        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-        L.hcb200_solver_copy_results(h, vp(tr), vp(cv), vp(inf))
-        tot = np.zeros(3, np.uint32)
-        L.hcb200_solver_totals(h, vp(tot))
-        per = np.zeros((H, 3), np.uint32)
-        L.hcb200_solver_per_hypothesis(h, vp(per))
-        best = np.zeros(16, np.int32)
-        found = ctypes.c_int()
-        res = np.zeros(4, np.float32)
-        L.hcb200_solver_best(h, vp(best), ctypes.cast(ctypes.byref(found), ctypes.c_void_p), vp(res))
-        sec = L.hcb200_solver_kernel_seconds(h)
-        sel_path = ctypes.c_int()
-        sel_sup = np.zeros(2, np.uint32)
-        L.hcb200_solver_selected.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
-        L.hcb200_solver_selected(h, ctypes.cast(ctypes.byref(sel_path), ctypes.c_void_p), vp(sel_sup))
-        L.hcb200_solver_free_round(h)
-        return dict(selected_path=sel_path.value, selected_support=sel_sup.tolist(), tracks=tr[..., 0] + 1j * tr[..., 1], conv=cv, inf=inf, totals=tot, per=per, best=best, pose_found=found.value,
-                    residuals=res, seconds=sec, H=H)
-
-    def close(self):
-        self.lib.hcb200_solver_destroy(self.h)
+from trifocal_pose_estimation_using_improved_gpuhc_b200.host_solver import HostSolver  # noqa: E402
 
 
 def test_host_class_default_round_matches_golden(tree):

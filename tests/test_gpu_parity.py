@@ -194,7 +194,7 @@ def test_device_refinement_bit_exact_vs_oracle(tracker, oracle, ransac0):
         assert _bit_equal(tr1[b, :30], x[:30]), b
         assert _bit_equal(np.array([sd, sx], np.float32), sums[b]), b
     # the ground-truth pose (hypothesis 0 / track 104) is a regular solution: the polish settles at the float floor
-    assert sums[104, 0] < 1e-9 * sums[104, 1]
+    assert sums[104, 0] < 1e-8 * sums[104, 1]
     # iters = 0: nothing moves
     tracker.refine_tracks(n_hyp, iters=0)
     tr2, _, _, _ = tracker.results(n_hyp)

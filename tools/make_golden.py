@@ -4,6 +4,9 @@
   ref_cpuhc_seed0_first6.npz     UNMODIFIED reference CPU-HC (oracle/_ref/libref_cpuhc.so): hypotheses 0..5 of the default
                                  run (seed 0, dataset 000): target params, per-path flags and end points
   ref_cpuhc_seed0_h100.npz       same binary, the full default run: per-path flags (bit-packed) + per-hypothesis counts
+  ref_cpuhc_pruned_seed0_h100.npz  the reference CPU-HC with the GPU kernels' path pruning patched in (oracle/_ref/libref_cpuhc_pruned.so,
+                                 SURVEY.md App. D.2): per-path flags of the default run — the reference's own CPU arithmetic under the
+                                 GPU kernels' control flow, one arm of the parity envelope
   ref_eval_vectors.npz           the reference's own evaluators / LAPACK cgesv on fixed inputs (Hx, H, Ht, solve)
   oracle_seed0_h100_{prune,noprune}.npz
                                  oracle/hc_oracle.c on the full default run: flags, counters, per-hypothesis counts and a
@@ -37,7 +40,7 @@ def main():
     prob, rs = fixtures.load_problem(), fixtures.load_ransac(0)
     orc = Oracle(prob)
     ref = ReferenceCPU()
-    what = sys.argv[1:] or ["ref6", "eval", "oracle", "ref100"]
+    what = sys.argv[1:] or ["ref6", "eval", "oracle", "ref100", "refpruned100"]
 
     with tempfile.TemporaryDirectory() as tmp:
         bindir = fixtures.materialize_tree(tmp, files=[0])
@@ -51,6 +54,16 @@ def main():
             np.savez_compressed(os.path.join(OUT, "ref_cpuhc_seed0_h100.npz"), converged_bits=np.packbits(cv), infinity_bits=np.packbits(inf),
                                 counts=counts.astype(np.int32), seconds=np.float64(sec), cores=np.int32(os.cpu_count()))
             print("ref100: %.1f s, totals conv/inf/real" % sec, counts.sum(0).tolist())
+
+    if "refpruned100" in what:
+        with tempfile.TemporaryDirectory() as tmp:
+            bindir = fixtures.materialize_tree(tmp, files=[0])
+            tr, cv, inf, tp, sec = ReferenceCPU(pruned=True).run(bindir, 100, seed=0, dataset_index=0)
+            counts = hc.count_solutions(tr, cv, inf, 100)
+            real = ((cv != 0) & np.all(np.abs(tr[:, :30].imag).astype(np.float64) <= 1e-4, axis=1)).astype(np.uint8)
+            np.savez_compressed(os.path.join(OUT, "ref_cpuhc_pruned_seed0_h100.npz"), converged_bits=np.packbits(cv), infinity_bits=np.packbits(inf),
+                                real_bits=np.packbits(real), counts=counts.astype(np.int32), seconds=np.float64(sec), cores=np.int32(os.cpu_count()))
+            print("refpruned100: %.1f s, totals conv/inf/real" % sec, counts.sum(0).tolist())
 
     if "eval" in what:
         rng = np.random.default_rng(12345)

@@ -24,7 +24,7 @@ _lib = None
 # every symbol include/hcb200.h declares
 ABI_SYMBOLS = ("hcb200_workspace_bytes", "hcb200_abi_version", "hcb200_track", "hcb200_track_abort",
                "hcb200_build_target_params", "hcb200_score_tracks", "hcb200_refine_tracks", "hcb200_kernel_info", "hcb200_ffma_probe",
-               "hcb200_error_string")
+               "hcb200_error_string", "hcb200_make_pose_record", "hcb200_reduce_pose_records")
 
 
 class HCB200Error(RuntimeError):
@@ -58,6 +58,10 @@ def load_library(path=None):
     lib.hcb200_score_tracks.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.hcb200_refine_tracks.restype = i32
     lib.hcb200_refine_tracks.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.hcb200_make_pose_record.restype = i32
+    lib.hcb200_make_pose_record.argtypes = [vp, vp, vp, vp, ctypes.c_longlong, i32, vp]
+    lib.hcb200_reduce_pose_records.restype = i32
+    lib.hcb200_reduce_pose_records.argtypes = [vp, i32, vp, vp]
     lib.hcb200_ffma_probe.restype = i32
     lib.hcb200_ffma_probe.argtypes = [vp, i32, vp, ctypes.POINTER(ctypes.c_double)]
     _lib = lib
@@ -266,6 +270,44 @@ class Tracker:
         torch.cuda.synchronize(self.device)
         return self.d_support[:n_paths].cpu().numpy(), self.d_best.cpu().numpy()
 
+    def score_tracks_async(self, n_hyp):
+        """Enqueue the device-side final scoring of the last round (no synchronisation); the best record lands in self.d_best."""
+        torch = self.torch
+        n_paths = n_hyp * NUM_TRACKS
+        if getattr(self, "d_support", None) is None or self.d_support.shape[0] < n_paths:
+            self.d_support = torch.empty((n_paths, 2), dtype=torch.int32, device=self.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            rc = self.lib.hcb200_score_tracks(self._stream(), n_paths, p(self.d_tracks), p(self.d_conv), self.n_edgels, p(self.d_edgels),
+                                              p(self.d_K), p(self.d_support), p(self.d_best), p(self.d_ws))
+        _check(rc, "hcb200_score_tracks")
+        self.launches += 2
+
+    def make_pose_record(self, path_offset, rank, abort=False):
+        """Enqueue: best record of the last score / abort launch -> the 128-byte exchange record self.d_pose_record (float32 [32])."""
+        torch = self.torch
+        if getattr(self, "d_pose_record", None) is None:
+            self.d_pose_record = torch.zeros(32, dtype=torch.float32, device=self.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            rc = self.lib.hcb200_make_pose_record(self._stream(), p(self.d_tracks), p(self.d_best), p(self.d_found) if abort else None,
+                                                  int(path_offset), int(rank), p(self.d_pose_record))
+        _check(rc, "hcb200_make_pose_record")
+        self.launches += 1
+        return self.d_pose_record
+
+    def reduce_pose_records(self, d_records, n):
+        """Enqueue the arg-max over n gathered 128-byte records ([n,32] float32 device tensor) -> self.d_round_record."""
+        torch = self.torch
+        if getattr(self, "d_round_record", None) is None:
+            self.d_round_record = torch.zeros(32, dtype=torch.float32, device=self.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            rc = self.lib.hcb200_reduce_pose_records(self._stream(), int(n), p(d_records), p(self.d_round_record))
+        _check(rc, "hcb200_reduce_pose_records")
+        self.launches += 1
+        return self.d_round_record
+
     def build_target_params(self, d_picked, d_tangents, n_hyp):
         p = lambda t: ctypes.c_void_p(t.data_ptr())
         with self.torch.cuda.device(self.device):
@@ -298,6 +340,15 @@ class Tracker:
         tracks = (tr[..., 0] + 1j * tr[..., 1]).astype(np.complex64)
         stats = self.d_stats[:n].cpu().numpy() if self.d_stats is not None else None
         return tracks, self.d_conv[:n].cpu().numpy(), self.d_inf[:n].cpu().numpy(), stats
+
+
+def decode_pose_record(rec):
+    """128-byte exchange record (float32 [32] host array, hcb200_pose_record) -> dict."""
+    b = np.ascontiguousarray(rec, np.float32).view(np.uint8)
+    i = b[:24].view(np.int32)
+    return {"found": int(i[0]), "inliers21": int(i[1]), "inliers31": int(i[2]), "n_candidates": int(i[3]), "abort_flag": int(i[4]),
+            "rank": int(i[5]), "path_id": int(b[24:32].view(np.int64)[0]), "R21": b[32:68].view(np.float32).reshape(3, 3).copy(),
+            "t21": b[68:80].view(np.float32).copy(), "R31": b[80:116].view(np.float32).reshape(3, 3).copy(), "t31": b[116:128].view(np.float32).copy()}
 
 
 def count_solutions(tracks, converged, infinity, n_hyp):
