@@ -87,6 +87,10 @@ bool Data_Reader::Read_dHdx_Indices(T*& h_dHdx_Index)
 {
   std::vector<int> v;
   if (!slurp(problem_dir_ + "/dHdx_indx.txt", v)) return false;
+  if (dHdx_capacity_ && v.size() != dHdx_capacity_) {       // the caller sized its table from the YAML keys: a file of another length is an error
+    hcb200::log_error("dHdx_indx.txt holds " + std::to_string(v.size()) + " indices, the settings file implies " + std::to_string(dHdx_capacity_));
+    return false;
+  }
   for (size_t i = 0; i < v.size(); i++) h_dHdx_Index[i] = (T)v[i];
   return true;
 }
@@ -96,6 +100,10 @@ bool Data_Reader::Read_dHdt_Indices(T*& h_dHdt_Index)
 {
   std::vector<int> v;
   if (!slurp(problem_dir_ + "/dHdt_indx.txt", v)) return false;
+  if (dHdt_capacity_ && v.size() != dHdt_capacity_) {
+    hcb200::log_error("dHdt_indx.txt holds " + std::to_string(v.size()) + " indices, the settings file implies " + std::to_string(dHdt_capacity_));
+    return false;
+  }
   for (size_t i = 0; i < v.size(); i++) h_dHdt_Index[i] = (T)v[i];
   return true;
 }

@@ -19,6 +19,9 @@ public:
   bool Read_Start_Sols(hcb200::complex32*& h_Start_Sols);              // 312 x 30 lines -> [312][31], entry 30 := 1
   bool Feed_Start_Sols_for_Intermediate_Homotopy(hcb200::complex32*& h_Start_Sols, hcb200::complex32*& h_Homotopy_Sols,
                                                  int RANSAC_Iters_per_GPU);
+  // sizes of the caller's index tables (dHdx_Max_Terms * dHdx_Max_Parts * vars^2, dHdt_Max_Terms * dHdt_Max_Parts * vars); once set,
+  // the two readers below refuse a file of any other length instead of writing past the table (the reference does not check)
+  void Set_Index_Table_Sizes(size_t dHdx_size, size_t dHdt_size) { dHdx_capacity_ = dHdx_size; dHdt_capacity_ = dHdt_size; }
   template <typename T> bool Read_dHdx_Indices(T*& h_dHdx_Index);
   template <typename T> bool Read_dHdt_Indices(T*& h_dHdt_Index);
   template <typename T> bool Read_unified_dHdx_dHdt_Indices(T*& h_unified, T* h_dHdx_Index, T* h_dHdt_Index, int dHdx_size, int dHdt_size);
@@ -35,6 +38,7 @@ public:
   static std::string padded_index(int index);                          // 7 -> "007"
 
 private:
+  size_t dHdx_capacity_ = 0, dHdt_capacity_ = 0;
   std::string problem_dir_, ransac_dir_;
   const int num_of_tracks, num_of_variables, num_of_params;
   std::vector<float> edgel_rows_;                                      // 12 floats per triplet, file order

@@ -60,6 +60,8 @@ GPU_HC_Solver::GPU_HC_Solver(YAML::Node cfg) : Problem_Setting_YAML_File(cfg)
   verbose                         = cfg.as_or<bool>("Verbose", true);
   device_scoring                  = cfg.as_or<bool>("Device_Scoring", true);
   refine_iterations               = cfg.as_or<int>("Refine_Iterations", 0);
+  const std::string dtp           = cfg.as_or<std::string>("Device_Target_Params", "auto");
+  device_target_params            = (dtp == "true") || (dtp == "auto" && num_ransac_iters >= 2048);
 
   if (HC_problem != "trifocal_2op1p_30x30" || Num_Of_Vars != HCB200_NUM_VARS || Num_Of_Params != HCB200_NUM_PARAMS ||
       Num_Of_Tracks != HCB200_NUM_TRACKS) {
@@ -127,6 +129,8 @@ void GPU_HC_Solver::Allocate_Arrays()
     HC_CUDA(cudaSetDevice(d.device));
     HC_CUDA(cudaMallocHost((void**)&h_Target_Params[g], sizeof(complex32) * P1 * (H ? H : 1)));
     HC_CUDA(cudaMallocHost((void**)&h_diffParams[g], sizeof(complex32) * P1 * (H ? H : 1)));
+    HC_CUDA(cudaMallocHost((void**)&h_picked[g], sizeof(int) * 3 * (H ? H : 1)));
+    if (device_target_params) HC_CUDA(cudaMalloc((void**)&d.d_picked, sizeof(int) * 3 * (H ? H : 1)));
     HC_CUDA(cudaMalloc((void**)&d.d_start_sols, sizeof(complex32) * Num_Of_Tracks * V1));
     HC_CUDA(cudaMalloc((void**)&d.d_start_params, sizeof(complex32) * P1));
     HC_CUDA(cudaMalloc((void**)&d.d_target, sizeof(complex32) * P1 * (H ? H : 1)));
@@ -148,6 +152,7 @@ void GPU_HC_Solver::Allocate_Arrays()
 bool GPU_HC_Solver::Read_Problem_Data()
 {
   Load_Problem_Data = std::make_shared<Data_Reader>(Problem_File_Path, RANSAC_Data_File_Path, Num_Of_Tracks, Num_Of_Vars, Num_Of_Params);
+  Load_Problem_Data->Set_Index_Table_Sizes((size_t)dHdx_Index_Size, (size_t)dHdt_Index_Size);
   if (!Load_Problem_Data->Read_Start_Params(h_Start_Params)) { hcb200::log_error("Start Parameters not loaded successfully!"); return false; }
   if (!Load_Problem_Data->Read_Start_Sols(h_Start_Sols)) { hcb200::log_error("Start Solutions not loaded successfully!"); return false; }
   // The evaluation-index tables are part of the problem definition the reference ships; the device code was generated from
@@ -181,6 +186,8 @@ void GPU_HC_Solver::Prepare_Target_Params(unsigned rand_seed_)
       unsigned e[3];
       do { for (int r = 0; r < 3; r++) e[r] = std::rand() % Num_Of_Triplet_Edgels; }
       while (!(e[0] != e[1] && e[1] != e[2]));          // the reference never tests e0 != e2
+      for (int r = 0; r < 3; r++) h_picked[g][(size_t)ti * 3 + r] = (int)e[r];
+      if (device_target_params) continue;               // the parameters themselves are gathered on the device (Data_Transfer_…)
       complex32* T = h_Target_Params[g] + (size_t)ti * P1;
       complex32* D = h_diffParams[g] + (size_t)ti * P1;
       for (int i = 0; i < 3; i++)
@@ -194,6 +201,28 @@ void GPU_HC_Solver::Prepare_Target_Params(unsigned rand_seed_)
       for (int i = 0; i < P1; i++) D[i] = hcb200::make_c32(T[i].x - h_Start_Params[i].x, T[i].y - h_Start_Params[i].y);
     }
   }
+  target_params_on_host = !device_target_params;
+}
+
+// Target parameters of GPU g as the host sees them; in device mode they are fetched from the GPU on first use.
+void GPU_HC_Solver::Fetch_Target_Params_To_Host()
+{
+  if (target_params_on_host) return;
+  DeviceGuard keep_callers_device;
+  const size_t P1 = Num_Of_Params + 1;
+  for (int g = 0; g < Num_Of_GPUs; g++) {
+    const size_t H = sub_RANSAC_iters[g];
+    if (!H) continue;
+    HC_CUDA(cudaSetDevice(shard[g].device));
+    HC_CUDA(cudaMemcpyAsync(h_Target_Params[g], shard[g].d_target, sizeof(complex32) * P1 * H, cudaMemcpyDeviceToHost, (cudaStream_t)shard[g].stream));
+    HC_CUDA(cudaMemcpyAsync(h_diffParams[g], shard[g].d_diff, sizeof(complex32) * P1 * H, cudaMemcpyDeviceToHost, (cudaStream_t)shard[g].stream));
+  }
+  for (int g = 0; g < Num_Of_GPUs; g++) {
+    if (!sub_RANSAC_iters[g]) continue;
+    HC_CUDA(cudaSetDevice(shard[g].device));
+    HC_CUDA(cudaStreamSynchronize((cudaStream_t)shard[g].stream));
+  }
+  target_params_on_host = true;
 }
 
 void GPU_HC_Solver::Set_RANSAC_Abort_Arrays()
@@ -220,32 +249,46 @@ void GPU_HC_Solver::Data_Transfer_From_Host_To_Device()
 {
   DeviceGuard keep_callers_device;
   const size_t V1 = Num_Of_Vars + 1, P1 = Num_Of_Params + 1;
-  for (int g = 0; g < Num_Of_GPUs; g++) {
+  const double t0 = wall_seconds();
+  for (int g = 0; g < Num_Of_GPUs; g++) {                  // enqueue every copy on every GPU first ...
     DeviceShard& d = shard[g];
     const size_t H = sub_RANSAC_iters[g], paths = H * Num_Of_Tracks;
     cudaStream_t s = (cudaStream_t)d.stream;
     HC_CUDA(cudaSetDevice(d.device));
-    const double t0 = wall_seconds();
     HC_CUDA(cudaMemcpyAsync(d.d_start_sols, h_Start_Sols, sizeof(complex32) * Num_Of_Tracks * V1, cudaMemcpyHostToDevice, s));
     HC_CUDA(cudaMemcpyAsync(d.d_start_params, h_Start_Params, sizeof(complex32) * P1, cudaMemcpyHostToDevice, s));
-    if (H) {
-      HC_CUDA(cudaMemcpyAsync(d.d_target, h_Target_Params[g], sizeof(complex32) * P1 * H, cudaMemcpyHostToDevice, s));
-      HC_CUDA(cudaMemcpyAsync(d.d_diff, h_diffParams[g], sizeof(complex32) * P1 * H, cudaMemcpyHostToDevice, s));
-    }
-    if (Abort_RANSAC_by_Good_Sol || device_scoring) {       // the edgel triplets feed the in-kernel abort test and the final scoring
+    if (Abort_RANSAC_by_Good_Sol || device_scoring || device_target_params) {   // the edgel triplets feed the abort test, the final scoring, the parameter gather
+      if (d.d_edgels && device_edgel_capacity < Num_Of_Triplet_Edgels) {        // a larger dataset file than the buffers were sized for
+        cudaFree(d.d_edgels); cudaFree(d.d_tangents); d.d_edgels = d.d_tangents = nullptr;
+      }
       if (!d.d_edgels) {
-        HC_CUDA(cudaMalloc((void**)&d.d_K, 9 * sizeof(float)));
+        if (!d.d_K) HC_CUDA(cudaMalloc((void**)&d.d_K, 9 * sizeof(float)));
         HC_CUDA(cudaMalloc((void**)&d.d_edgels, (size_t)Num_Of_Triplet_Edgels * 6 * sizeof(float)));
+        HC_CUDA(cudaMalloc((void**)&d.d_tangents, (size_t)Num_Of_Triplet_Edgels * 6 * sizeof(float)));
         device_edgels_allocated = true;
       }
       HC_CUDA(cudaMemcpyAsync(d.d_edgels, h_Triplet_Edge_Locations, (size_t)Num_Of_Triplet_Edgels * 6 * sizeof(float), cudaMemcpyHostToDevice, s));
       HC_CUDA(cudaMemcpyAsync(d.d_K, h_Camera_Intrinsic_Matrix, 9 * sizeof(float), cudaMemcpyHostToDevice, s));
     }
+    if (H && !device_target_params) {
+      HC_CUDA(cudaMemcpyAsync(d.d_target, h_Target_Params[g], sizeof(complex32) * P1 * H, cudaMemcpyHostToDevice, s));
+      HC_CUDA(cudaMemcpyAsync(d.d_diff, h_diffParams[g], sizeof(complex32) * P1 * H, cudaMemcpyHostToDevice, s));
+    } else if (H) {       // 12 bytes per hypothesis go over PCIe; the 34 parameters and target - start are gathered on the GPU
+      HC_CUDA(cudaMemcpyAsync(d.d_tangents, h_Triplet_Edge_Tangents, (size_t)Num_Of_Triplet_Edgels * 6 * sizeof(float), cudaMemcpyHostToDevice, s));
+      HC_CUDA(cudaMemcpyAsync(d.d_picked, h_picked[g], sizeof(int) * 3 * H, cudaMemcpyHostToDevice, s));
+      const int rc = hcb200_build_target_params(d.stream, (int)H, d.d_picked, Num_Of_Triplet_Edgels, d.d_edgels, d.d_tangents,
+                                                (const float*)d.d_start_params, (float*)d.d_target, (float*)d.d_diff);
+      if (rc != 0) { std::fprintf(stderr, "[ERROR] target-parameter launch failed on GPU %d: %s\n", g, hcb200_error_string(rc)); std::exit(2); }
+    }
     if (Abort_RANSAC_by_Good_Sol) {
       if (paths) HC_CUDA(cudaMemcpyAsync(d.d_found_index, h_Trifocal_Sols_Batch_Index[g], paths * sizeof(int), cudaMemcpyHostToDevice, s));
       HC_CUDA(cudaMemcpyAsync(d.d_found, h_Found_Trifocal_Sols[g], sizeof(bool), cudaMemcpyHostToDevice, s));
     }
-    HC_CUDA(cudaStreamSynchronize(s));
+  }
+  device_edgel_capacity = std::max(device_edgel_capacity, Num_Of_Triplet_Edgels);
+  for (int g = 0; g < Num_Of_GPUs; g++) {                  // ... then wait for all of them
+    HC_CUDA(cudaSetDevice(shard[g].device));
+    HC_CUDA(cudaStreamSynchronize((cudaStream_t)shard[g].stream));
     transfer_h2d_time[g] = wall_seconds() - t0;
   }
 }
@@ -299,6 +342,7 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
   }
 
   // results: every GPU copies straight into its slice of the stacked host arrays (reference: per-GPU copies + memcpy, :449-506)
+  const double t0_d2h = wall_seconds();
   for (int g = 0; g < Num_Of_GPUs; g++) {
     DeviceShard& d = shard[g];
     const size_t paths = (size_t)sub_RANSAC_iters[g] * Num_Of_Tracks;
@@ -308,7 +352,6 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
     float ms = 0.f;
     HC_CUDA(cudaEventElapsedTime(&ms, (cudaEvent_t)d.ev_start, (cudaEvent_t)d.ev_stop));
     gpu_time[g] = ms * 1e-3;
-    const double t0 = wall_seconds();
     HC_CUDA(cudaMemcpyAsync(h_GPU_HC_Track_Sols_Stack + (size_t)d.path_offset * V1, d.d_tracks, sizeof(complex32) * V1 * paths, cudaMemcpyDeviceToHost, s));
     HC_CUDA(cudaMemcpyAsync(h_is_GPU_HC_Sol_Converge_Stack + d.path_offset, d.d_conv, paths, cudaMemcpyDeviceToHost, s));
     HC_CUDA(cudaMemcpyAsync(h_is_GPU_HC_Sol_Infinity_Stack + d.path_offset, d.d_inf, paths, cudaMemcpyDeviceToHost, s));
@@ -317,8 +360,12 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
       HC_CUDA(cudaMemcpyAsync(h_Trifocal_Sols_Batch_Index[g], d.d_found_index, paths * sizeof(int), cudaMemcpyDeviceToHost, s));
       HC_CUDA(cudaMemcpyAsync(h_best[g], d.d_best, sizeof(hcb200_best_record), cudaMemcpyDeviceToHost, s));
     }
-    HC_CUDA(cudaStreamSynchronize(s));
-    transfer_d2h_time[g] = wall_seconds() - t0;
+  }
+  for (int g = 0; g < Num_Of_GPUs; g++) {               // all GPUs copy at the same time; wait once for each
+    if (!sub_RANSAC_iters[g]) continue;
+    HC_CUDA(cudaSetDevice(shard[g].device));
+    HC_CUDA(cudaStreamSynchronize((cudaStream_t)shard[g].stream));
+    transfer_d2h_time[g] = wall_seconds() - t0_d2h;
   }
 
   // tiny gather: the best record of every GPU, reduced on the host (smallest global path id wins)
@@ -437,10 +484,11 @@ void GPU_HC_Solver::Free_Triplet_Edgels_Mem()
   if (device_edgels_allocated) {
     for (int g = 0; g < Num_Of_GPUs; g++) {
       cudaSetDevice(shard[g].device);
-      cudaFree(shard[g].d_edgels); cudaFree(shard[g].d_K);
-      shard[g].d_edgels = shard[g].d_K = nullptr;
+      cudaFree(shard[g].d_edgels); cudaFree(shard[g].d_K); cudaFree(shard[g].d_tangents);
+      shard[g].d_edgels = shard[g].d_K = shard[g].d_tangents = nullptr;
     }
     device_edgels_allocated = false;
+    device_edgel_capacity = 0;
   }
   if (!edgels_allocated) return;
   delete[] h_Triplet_Edge_Locations; delete[] h_Triplet_Edge_Tangents;
@@ -460,7 +508,8 @@ GPU_HC_Solver::~GPU_HC_Solver()
     if (arrays_allocated) {
       cudaFree(d.d_start_sols); cudaFree(d.d_start_params); cudaFree(d.d_target); cudaFree(d.d_diff); cudaFree(d.d_tracks);
       cudaFree(d.d_conv); cudaFree(d.d_inf); cudaFree(d.d_ws); cudaFree(d.d_support); cudaFree(d.d_score_best); cudaFree(d.d_refine_sums);
-      cudaFreeHost(h_Target_Params[g]); cudaFreeHost(h_diffParams[g]); cudaFreeHost(h_score_best[g]);
+      cudaFreeHost(h_Target_Params[g]); cudaFreeHost(h_diffParams[g]); cudaFreeHost(h_score_best[g]); cudaFreeHost(h_picked[g]);
+      cudaFree(d.d_picked);
     }
     cudaEventDestroy((cudaEvent_t)d.ev_start); cudaEventDestroy((cudaEvent_t)d.ev_stop);
     cudaStreamDestroy((cudaStream_t)d.stream);

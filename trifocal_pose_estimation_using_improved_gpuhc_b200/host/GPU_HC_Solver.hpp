@@ -59,7 +59,9 @@ public:
   const hcb200::complex32* Track_Sols() const { return h_GPU_HC_Track_Sols_Stack; }     // [H*312][31]
   const bool* Sol_Converge() const { return h_is_GPU_HC_Sol_Converge_Stack; }
   const bool* Sol_Infinity() const { return h_is_GPU_HC_Sol_Infinity_Stack; }
-  const hcb200::complex32* Target_Params(int gpu_id) const { return h_Target_Params[gpu_id]; }
+  const hcb200::complex32* Target_Params(int gpu_id) { Fetch_Target_Params_To_Host(); return h_Target_Params[gpu_id]; }
+  void Fetch_Target_Params_To_Host();    // device-side Prepare_Target_Params: bring the parameters back when the host asks for them
+  const int* Picked_Edgels(int gpu_id) const { return h_picked[gpu_id]; }     // [H_g][3] edgel indices drawn by the rand() stream
   const std::vector<std::array<unsigned, 3>>& Per_Hypothesis_Counts() const { return per_hypothesis_counts; }
   const hcb200_best_record& Best_Record() const { return best_record; }                 // path_id is GLOBAL (stacked) numbering
   const std::vector<int>& Found_Path_Ids() const { return found_path_ids; }
@@ -80,6 +82,8 @@ private:
     unsigned char *d_conv = nullptr, *d_inf = nullptr, *d_found = nullptr;
     void* d_ws = nullptr;
     float *d_edgels = nullptr, *d_K = nullptr;
+    float* d_tangents = nullptr;       // device-side Prepare_Target_Params: edgel tangents and the picked edgel triplets of this shard
+    int* d_picked = nullptr;
     int* d_found_index = nullptr;
     hcb200_best_record* d_best = nullptr;
     int* d_support = nullptr;                 // [paths][2] inlier supports from hcb200_score_tracks
@@ -128,6 +132,12 @@ private:
   int refine_iterations = 0;        // Newton refinement of converged end points on the GPU before they are copied back
                                     // (YAML key Refine_Iterations; 0 = the reference's behaviour)
   bool device_edgels_allocated = false;
+  // Prepare_Target_Params on the device (hcb200_build_target_params): the host keeps the glibc rand() stream and ships 12 bytes per
+  // hypothesis instead of 544.  YAML key Device_Target_Params: auto (default: from 2048 hypotheses up) | true | false.
+  bool device_target_params = false;
+  bool target_params_on_host = true;     // h_Target_Params / h_diffParams hold this round's values
+  int* h_picked[MAX_NUM_OF_GPUS] = {nullptr};
+  int device_edgel_capacity = 0;
 
   std::vector<std::array<unsigned, 3>> per_hypothesis_counts;
   hcb200_best_record best_record{};
