@@ -40,9 +40,9 @@ NOMINAL_FP32_TFLOPS = 74.4     # 148 SMs x 128 lanes x 2 flop x 1.965 GHz
 # Executed FP32 work of the FINAL kernel, from its ncu capture (profiles/ncu_r2.md): thread-level FFMA/FMUL/FADD executed per HC stage
 # (smsp__sass_thread_inst_executed_op_f{fma,mul,add}_pred_on.sum / stages; an FMA counts 2 flop) — what the FP32 pipe really did,
 # beside the dense-LU model above, which also counts the structural zeros the kernel skips.
-EXEC_FLOP_PER_STAGE = 55500.0
+EXEC_FLOP_PER_STAGE = 54772.0
 EXEC_SOURCE = "profiles/ncu_r2.md: executed FP32 thread instructions of the final kernel per HC stage (FMA = 2 flop), x stages / kernel time"
-TRAFFIC_BYTES_H100 = 1755904
+TRAFFIC_BYTES_H100 = 199168
 TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one tracker launch of the default round, ncu --set full capture of the final "
                   "kernel (profiles/ncu_r2.md); the 7.8 MB of results stay in the 126 MB L2, so traffic < algorithmic bytes")
 

@@ -16,6 +16,7 @@ ORACLE_SO = os.path.join(HERE, "liboracle_hc.so")
 REF_CPU_SO = os.path.join(HERE, "_ref", "libref_cpuhc.so")
 REF_CPU_PRUNED_SO = os.path.join(HERE, "_ref", "libref_cpuhc_pruned.so")   # reference CPU-HC + the GPU kernels' path pruning (generated copy)
 REF_GPU_SO = os.path.join(HERE, "_ref", "libref_gpuhc.so")
+REF_GPU_DEBUG_SO = os.path.join(HERE, "_ref", "libref_gpuhc_debug.so")     # same sources with the reference's GPU_DEBUG switch on
 
 N, NP1, TRACKS = 30, 34, 312
 
@@ -190,12 +191,13 @@ class ReferenceGPU:
     """The UNMODIFIED reference GPU-HC++ kernels compiled for sm_100a (oracle/_ref/libref_gpuhc.so), driven the way
     GPU_HC_Solver drives them.  GPU box only; used as the GPU baseline in bench.py and as a second oracle in tests."""
 
-    def __init__(self, problem, device="cuda:0"):
+    def __init__(self, problem, device="cuda:0", debug=False):
         import torch
-        if not os.path.exists(REF_GPU_SO):
-            raise FileNotFoundError(REF_GPU_SO + " (run `make -C oracle ref` in the build container)")
+        so = REF_GPU_DEBUG_SO if debug else REF_GPU_SO
+        if not os.path.exists(so):
+            raise FileNotFoundError(so + " (run `make -C oracle ref` in the build container)")
         self.torch = torch
-        self.lib = ctypes.CDLL(REF_GPU_SO)
+        self.lib = ctypes.CDLL(so)
         self.device = torch.device(device)
         ss = np.ones((TRACKS, N + 1), np.complex64)
         ss[:, :N] = problem["start_sols"]
@@ -253,6 +255,11 @@ class ReferenceGPU:
                                             p(self.d_conv), p(self.d_inf), p(self.d_dbg), p(self.d_found), p(self.d_found_index))
         if rc:
             raise RuntimeError("ref_gpuhc_track_abort -> cudaError %d" % rc)
+
+    def debug_t0_dt(self):
+        """GPU_DEBUG build only: per path (1, 0) if converged else (t0, delta_t) at the end of the track (…TrunPaths.cu:287-289)."""
+        self.torch.cuda.synchronize(self.device)
+        return self.d_dbg.cpu().numpy()
 
     def results(self):
         self.torch.cuda.synchronize(self.device)

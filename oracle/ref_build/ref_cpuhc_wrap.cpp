@@ -26,6 +26,7 @@ int g_hcb200_ref_num_hyp = 100;   // read through the NUM_OF_RANSAC_ITERATIONS m
 #define private public
 #define class struct
 #include "CPU_HC_Solver.hpp"
+#include "util.hpp"
 #undef class
 #undef private
 
@@ -95,5 +96,54 @@ void ref_eval_H(const int* dHdt_index, const float* x31, const float* p34, float
 // LAPACK cgesv exactly as the reference calls it (CPUHC_Generic_Solver_Eval_by_Indx.cpp:93); A column-major, overwritten.
 int ref_cgesv(float* A900, float* b30)
 { int n = 30, nrhs = 1, info = 0, ipiv[30]; lapackf77_cgesv(&n, &nrhs, (magmaFloatComplex*)A900, &n, ipiv, (magmaFloatComplex*)b30, &n, &info); return info; }
+
+// Support counting of ONE end point with the reference's own MVG helpers (class util, magmaHC/util.hpp:29-209), called the way
+// Evaluations::Transform_GPUHC_Sols_to_Trifocal_Relative_Pose + ::get_Solution_with_Maximal_Support (Evaluations.cpp:298-504) call them,
+// but with the candidate's own end point (the reference indexes the first track for every candidate).  Returns 1
+// if the path passes the reference's candidate gates (:317-335): |Im| of the six Cayley parameters < IMAG_PART_TOL, eight depths >= 0.
+// pose24 = R21 (9, row-major), t21 (3), R31 (9), t31 (3) as the reference normalises them.  This pins the arithmetic of
+// hcb200_score_tracks / host/mvg.hpp to util.hpp (tests/golden/ref_util_support.npz).
+int ref_util_support(const float* x31_re_im, const float* locations, int n_edgels, const float* K9, int* n21, int* n31, float* pose24)
+{
+  *n21 = 0; *n31 = 0;
+  const magmaFloatComplex* x = (const magmaFloatComplex*)x31_re_im;
+  for (int vi = 0; vi < 6; vi++) if (!(fabs(MAGMA_C_IMAG(x[24 + vi])) < IMAG_PART_TOL)) return 0;
+  for (int di = 0; di < 8; di++) if (!(MAGMA_C_REAL(x[di]) >= 0)) return 0;
+  util u;
+  float* t21 = new float[3]; float* t31 = new float[3]; float* R21 = new float[9]; float* R31 = new float[9];
+  float r21[3], r31[3], K[9];
+  for (int i = 0; i < 3; i++) { t21[i] = MAGMA_C_REAL(x[18 + i]); t31[i] = MAGMA_C_REAL(x[21 + i]); r21[i] = MAGMA_C_REAL(x[24 + i]); r31[i] = MAGMA_C_REAL(x[27 + i]); }
+  for (int i = 0; i < 9; i++) K[i] = K9[i];
+  u.Normalize_Translation_Vector(t21);
+  u.Normalize_Translation_Vector(t31);
+  u.Cayley_To_Rotation_Matrix(r21, R21);
+  u.Cayley_To_Rotation_Matrix(r31, R31);
+  for (int i = 0; i < 9; i++) { pose24[i] = R21[i]; pose24[12 + i] = R31[i]; }
+  for (int i = 0; i < 3; i++) { pose24[9 + i] = t21[i]; pose24[21 + i] = t31[i]; }
+  float g1[3], g2[3], g3[3];
+  for (int ei = 0; ei < n_edgels; ei++) {
+    const float* e = locations + (size_t)ei * 6;
+    g1[0] = e[0]; g1[1] = e[1]; g1[2] = 1.0f; g2[0] = e[2]; g2[1] = e[3]; g2[2] = 1.0f; g3[0] = e[4]; g3[1] = e[5]; g3[2] = 1.0f;
+    const float rho21 = u.get_depth_rho(g1, g2, R21, t21);
+    const float err21 = u.get_Reprojection_Pixels_Error(g1, g2, R21, t21, K, rho21);
+    const float rho31 = u.get_depth_rho(g1, g3, R31, t31);
+    const float err31 = u.get_Reprojection_Pixels_Error(g1, g3, R31, t31, K, rho31);
+    if (err21 < REPROJ_ERROR_INLIER_THRESH) (*n21)++;
+    if (err31 < REPROJ_ERROR_INLIER_THRESH) (*n31)++;
+  }
+  delete[] t21; delete[] t31; delete[] R21; delete[] R31;
+  return 1;
+}
+
+// the two helpers on their own (util.hpp:169-209), for value-level goldens: out = (rho, reprojection error in pixels)
+void ref_util_pair(const float* gamma1, const float* gamma2, const float* R9, const float* T3, const float* K9, float* out2)
+{
+  util u;
+  float g1[3] = {gamma1[0], gamma1[1], 1.0f}, g2[3] = {gamma2[0], gamma2[1], 1.0f}, R[9], T[3], K[9];
+  for (int i = 0; i < 9; i++) { R[i] = R9[i]; K[i] = K9[i]; }
+  for (int i = 0; i < 3; i++) T[i] = T3[i];
+  out2[0] = u.get_depth_rho(g1, g2, R, T);
+  out2[1] = u.get_Reprojection_Pixels_Error(g1, g2, R, T, K, out2[0]);
+}
 
 }  // extern "C"

@@ -301,6 +301,31 @@ def test_device_scoring_matches_host_evaluations(problem, ransac0, default_round
     assert (best[2], best[3]) == (5117, 5117)
 
 
+def test_device_scoring_is_pinned_to_the_reference_util(problem, ransac0, default_round):
+    """(f2) hcb200_score_tracks against the REFERENCE's MVG helpers (magmaHC/util.hpp:29-209 through oracle/_ref/libref_cpuhc.so; golden
+    tests/golden/ref_util_support.npz): same candidates, same selected pose, inlier counts identical on >= 34 of the 36 candidates and
+    within one edgel on the rest (the reference binary is FMA-contracted, the kernel is not: tests/test_host_cpu.py), and the pose in
+    the 128-byte exchange record equals the reference's normalised (R21, t21, R31, t31) to float rounding."""
+    picked, target, diff = default_round
+    g = np.load(os.path.join(GOLD, "ref_util_support.npz"))
+    trk = hc.Tracker(problem=problem)
+    trk.set_edgels(ransac0["locations"], ransac0["K"])
+    trk.upload_params(target, diff)
+    trk.track(100, prune=True)
+    support, best = trk.score_tracks(100)
+    assert np.array_equal(support[:, 0] >= 0, g["support"][:, 0] >= 0)              # the same candidate set
+    d = np.abs(support - g["support"]).max(1)
+    assert d.max() <= 1 and (d[g["candidates"]] == 0).sum() >= 34 and d[104] == 0
+    assert best[0] == 1 and best[1] == 104 and best[4] == len(g["candidates"])
+    import torch
+    rec = hc.decode_pose_record(trk.make_pose_record(0, 0).cpu().numpy())
+    torch.cuda.synchronize()
+    ref_pose = g["poses"][g["candidates"].tolist().index(104)]
+    mine = np.concatenate([rec["R21"].reshape(-1), rec["t21"], rec["R31"].reshape(-1), rec["t31"]])
+    assert rec["path_id"] == 104 and (rec["inliers21"], rec["inliers31"]) == (5117, 5117)
+    assert np.abs(mine - ref_pose).max() < 2e-6
+
+
 def test_launch_is_stream_ordered_and_graph_capturable(problem, default_round):
     """The C ABI only ENQUEUES (workspace reset + one kernel) on the caller's stream — no synchronisation, no allocation — so a round
     can be captured in a CUDA graph and replayed; the replay gives the same bits as a direct launch."""

@@ -10,7 +10,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle.pyoracle import ReferenceGPU
+from oracle.pyoracle import ReferenceGPU, REF_GPU_DEBUG_SO
 from trifocal_pose_estimation_using_improved_gpuhc_b200 import fixtures, hc
 
 prefix = sys.argv[1]
@@ -18,6 +18,13 @@ prob, rs = fixtures.load_problem(), fixtures.load_ransac(0)
 for H in [int(a) for a in sys.argv[2:]] or [100]:
     picked = hc.sample_hypotheses(0, H, rs["locations"].shape[0])
     target, diff = hc.target_params_from_picks(picked, rs["locations"], rs["tangents"], prob["start_params"])
+    dbg = None
+    if os.path.exists(REF_GPU_DEBUG_SO):      # the reference's own GPU_DEBUG output: (t0, delta_t) of every path that did not converge
+        rd = ReferenceGPU(prob, debug=True)
+        rd.setup(target, diff, rs["locations"], rs["K"])
+        rd.track()
+        dbg = rd.debug_t0_dt()
+        del rd
     ref = ReferenceGPU(prob)
     ref.setup(target, diff, rs["locations"], rs["K"])
     runs = []
@@ -34,6 +41,8 @@ for H in [int(a) for a in sys.argv[2:]] or [100]:
     tr, cv, inf, st = trk.results(H)
     out = dict(picked=picked, ref_conv=np.packbits(cv_r), ref_inf=np.packbits(inf_r), our_conv=np.packbits(cv), our_inf=np.packbits(inf),
                our_stats=st.astype(np.int32), ref_deterministic=np.array([det]))
+    if dbg is not None:
+        out["ref_debug_t0_dt"] = dbg.astype(np.float32)
     if H <= 100:
         out.update(ref_tracks=tr_r[:, :30], our_tracks=tr[:, :30])
     else:        # end points only where either side converged, as float32 pairs (keeps the file small)

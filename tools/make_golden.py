@@ -7,6 +7,9 @@
   ref_cpuhc_pruned_seed0_h100.npz  the reference CPU-HC with the GPU kernels' path pruning patched in (oracle/_ref/libref_cpuhc_pruned.so,
                                  SURVEY.md App. D.2): per-path flags of the default run — the reference's own CPU arithmetic under the
                                  GPU kernels' control flow, one arm of the parity envelope
+  ref_util_support.npz           the reference's MVG helpers (util.hpp:29-209, through oracle/_ref/libref_cpuhc.so): candidate gate, inlier
+                                 counts and normalised pose of every converged end point of the default round (oracle tracks, pruning on),
+                                 plus value-level (rho, reprojection error) vectors — pins hcb200_score_tracks / host/mvg.hpp to the reference
   ref_eval_vectors.npz           the reference's own evaluators / LAPACK cgesv on fixed inputs (Hx, H, Ht, solve)
   oracle_seed0_h100_{prune,noprune}.npz
                                  oracle/hc_oracle.c on the full default run: flags, counters, per-hypothesis counts and a
@@ -40,7 +43,7 @@ def main():
     prob, rs = fixtures.load_problem(), fixtures.load_ransac(0)
     orc = Oracle(prob)
     ref = ReferenceCPU()
-    what = sys.argv[1:] or ["ref6", "eval", "oracle", "ref100", "refpruned100"]
+    what = sys.argv[1:] or ["ref6", "eval", "oracle", "ref100", "refpruned100", "refutil"]
 
     with tempfile.TemporaryDirectory() as tmp:
         bindir = fixtures.materialize_tree(tmp, files=[0])
@@ -64,6 +67,36 @@ def main():
             np.savez_compressed(os.path.join(OUT, "ref_cpuhc_pruned_seed0_h100.npz"), converged_bits=np.packbits(cv), infinity_bits=np.packbits(inf),
                                 real_bits=np.packbits(real), counts=counts.astype(np.int32), seconds=np.float64(sec), cores=np.int32(os.cpu_count()))
             print("refpruned100: %.1f s, totals conv/inf/real" % sec, counts.sum(0).tolist())
+
+    if "refutil" in what:
+        import ctypes
+        from oracle.pyoracle import REF_CPU_SO, c2f
+        lib = ctypes.CDLL(REF_CPU_SO)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        tgt, dif, picked = orc.prepare_target_params(0, 100, rs["locations"], rs["tangents"])
+        tr, cv, inf, st = orc.track(tgt, dif, True)
+        loc = np.ascontiguousarray(rs["locations"], np.float32)
+        K = np.ascontiguousarray(rs["K"], np.float32).reshape(-1)
+        support = np.full((31200, 2), -1, np.int32)
+        poses, cand = [], []
+        for pth in np.nonzero(cv)[0]:
+            a, b, pose = ctypes.c_int(), ctypes.c_int(), np.zeros(24, np.float32)
+            if lib.ref_util_support(vp(c2f(tr[pth])), vp(loc), loc.shape[0], vp(K), ctypes.byref(a), ctypes.byref(b), vp(pose)):
+                support[pth] = (a.value, b.value)
+                cand.append(pth); poses.append(pose)
+        rng = np.random.default_rng(7)
+        g1, g2 = rng.normal(0, 0.3, (64, 2)).astype(np.float32), rng.normal(0, 0.3, (64, 2)).astype(np.float32)
+        pairs = np.zeros((64, 2), np.float32)
+        Rs, Ts = [], []
+        for k in range(64):
+            pose = poses[k % len(poses)]
+            R, T = np.ascontiguousarray(pose[0:9]), np.ascontiguousarray(pose[9:12])
+            lib.ref_util_pair(vp(g1[k]), vp(g2[k]), vp(R), vp(T), vp(K), vp(pairs[k]))
+            Rs.append(R.copy()); Ts.append(T.copy())
+        np.savez_compressed(os.path.join(OUT, "ref_util_support.npz"), support=support, candidates=np.array(cand, np.int32), poses=np.array(poses),
+                            converged_bits=np.packbits(cv), g1=g1, g2=g2, R=np.array(Rs), T=np.array(Ts), K=K, rho_err=pairs)
+        best = max(cand, key=lambda q: (min(support[q]), -q))
+        print("refutil: %d candidates among %d converged paths; best path %d support %s" % (len(cand), int(cv.sum()), best, support[best].tolist()))
 
     if "eval" in what:
         rng = np.random.default_rng(12345)

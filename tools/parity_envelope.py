@@ -42,6 +42,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--hyp", type=int, default=100)
     ap.add_argument("--seeds", type=int, default=64, help="number of stochastic-arithmetic variants")
+    ap.add_argument("--seed-start", type=int, default=1, help="first stochastic-arithmetic seed (to extend an earlier run)")
+    ap.add_argument("--structured", type=int, default=1, help="0: skip the structured variants except the spec (extension runs)")
     ap.add_argument("--sampler-seed", type=int, default=0)
     ap.add_argument("--dataset", type=int, default=0)
     ap.add_argument("--no-prune", action="store_true")
@@ -53,7 +55,8 @@ def main():
     H, P = a.hyp, a.hyp * 312
     picked = hc.sample_hypotheses(a.sampler_seed, H, rs["locations"].shape[0])
     target, diff = hc.target_params_from_picks(picked, rs["locations"], rs["tangents"], prob["start_params"])
-    variants = list(STRUCTURED) + [("ulp perturbation seed %d" % s, dict(perturb_seed=s)) for s in range(1, a.seeds + 1)]
+    variants = (list(STRUCTURED) if a.structured else STRUCTURED[:1]) + \
+        [("ulp perturbation seed %d" % s, dict(perturb_seed=s)) for s in range(a.seed_start, a.seed_start + a.seeds)]
     conv, inf, real, steps = [], [], [], []
     t0 = time.time()
     for name, v in variants:
