@@ -351,6 +351,36 @@ def decode_pose_record(rec):
             "t21": b[68:80].view(np.float32).copy(), "R31": b[80:116].view(np.float32).reshape(3, 3).copy(), "t31": b[116:128].view(np.float32).copy()}
 
 
+def encode_pose_record(found, inliers21, inliers31, n_candidates, abort_flag, rank, path_id, pose24=None):
+    """Build a 128-byte exchange record (hcb200_pose_record) on the host; returns float32 [32]."""
+    b = np.zeros(128, np.uint8)
+    b[:24].view(np.int32)[:] = [found, inliers21, inliers31, n_candidates, abort_flag, rank]
+    b[24:32].view(np.int64)[0] = path_id
+    if pose24 is not None:
+        b[32:128].view(np.float32)[:] = np.asarray(pose24, np.float32).reshape(24)
+    return b.view(np.float32).copy()
+
+
+def reduce_pose_records_host(records):
+    """Host mirror of hcb200_reduce_pose_records (csrc/hc_tracker.cu): arg-max over the gathered records — largest
+    min(inliers21, inliers31), lowest global path id among equals; abort flags OR-ed, candidate counts summed.
+    records: float32 [n, 32].  Returns the winning record as a dict (decode_pose_record layout)."""
+    recs = [decode_pose_record(r) for r in np.asarray(records, np.float32).reshape(-1, 32)]
+    best = None
+    for r in recs:
+        if not (r["found"] and r["path_id"] >= 0):
+            continue
+        key = (min(r["inliers21"], r["inliers31"]), -r["path_id"])
+        if best is None or key > best[0]:
+            best = (key, r)
+    out = dict(best[1]) if best else {"found": 0, "inliers21": 0, "inliers31": 0, "rank": -1, "path_id": -1,
+                                     "R21": np.zeros((3, 3), np.float32), "t21": np.zeros(3, np.float32),
+                                     "R31": np.zeros((3, 3), np.float32), "t31": np.zeros(3, np.float32)}
+    out["n_candidates"] = sum(r["n_candidates"] for r in recs)
+    out["abort_flag"] = int(any(r["abort_flag"] for r in recs))
+    return out
+
+
 def count_solutions(tracks, converged, infinity, n_hyp):
     """Evaluations::Evaluate_HC_Sols (Evaluations.cpp:145-167): per hypothesis (#converged, #infinity, #real) with
     real == converged and all 30 |imag| <= 1e-4 (ZERO_IMAG_PART_TOL_FOR_SP)."""

@@ -113,6 +113,7 @@ void GPU_HC_Solver::check_multiGPUs()
 
 void GPU_HC_Solver::Allocate_Arrays()
 {
+  if (arrays_allocated) return;          // sizes are fixed by the settings file: a second call (one per round in some drivers) is a no-op
   DeviceGuard keep_callers_device;
   const size_t V1 = Num_Of_Vars + 1, P1 = Num_Of_Params + 1, n_paths = (size_t)Num_Of_Paths();
   h_Start_Sols   = (complex32*)std::malloc(sizeof(complex32) * Num_Of_Tracks * V1);
