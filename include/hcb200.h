@@ -115,6 +115,12 @@ int hcb200_score_tracks(void* stream, int n_paths, const float* d_tracks, const 
                         const float* d_edgel_locations, const float* d_intrinsic, int32_t* d_support,
                         hcb200_best_record* d_best, void* d_workspace);
 
+/* Evaluations::Evaluate_HC_Sols on the device (reference Evaluations.cpp:145-167): d_counts[3*h + {0,1,2}] = number of converged,
+ * infinity-failed and real (converged, all 30 |imag| <= 1e-4) paths of hypothesis h.  Lets a host driver report the round's
+ * statistics without walking 248 bytes per path on the CPU. */
+int hcb200_count_solutions(void* stream, int n_hyp, const float* d_tracks, const uint8_t* d_converged, const uint8_t* d_infinity,
+                           unsigned int* d_counts);
+
 /* Multi-GPU result exchange, device side.  hcb200_make_pose_record turns the best record of the last score / abort launch on
  * this GPU into the 128-byte exchange record (pose from the track's Cayley parameters, host/mvg.hpp arithmetic; path_offset =
  * 312 * first hypothesis of this GPU's shard; d_found may be NULL).  hcb200_reduce_pose_records reduces n <= 32 gathered records

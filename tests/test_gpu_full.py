@@ -301,6 +301,40 @@ def test_device_scoring_matches_host_evaluations(problem, ransac0, default_round
     assert (best[2], best[3]) == (5117, 5117)
 
 
+def test_device_statistics_equal_host_statistics(tree, problem, default_round):
+    """hcb200_count_solutions (per-hypothesis converged / infinity / real counts reduced on the GPU) against the host's walk over every end
+    point (Evaluations::Evaluate_HC_Sols, reference Evaluations.cpp:145-167) and against hc.count_solutions, and the host class gives the
+    same round statistics with Device_Statistics on and off."""
+    picked, target, diff = default_round
+    trk = hc.Tracker(problem=problem)
+    trk.upload_params(target, diff)
+    trk.track(100, prune=True)
+    tr, cv, inf, _ = trk.results(100)
+    assert np.array_equal(trk.count_solutions_device(100), hc.count_solutions(tr, cv, inf, 100))
+    a = HostSolver(tree, "Num_Of_GPUs=1;Device_Statistics=true")
+    ra = a.round()
+    a.close()
+    b = HostSolver(tree, "Num_Of_GPUs=1;Device_Statistics=false")
+    rb = b.round()
+    b.close()
+    assert np.array_equal(ra["per"], rb["per"]) and np.array_equal(ra["totals"], rb["totals"])
+    assert np.array_equal(ra["per"].astype(np.int64), hc.count_solutions(tr, cv, inf, 100))
+
+
+def test_lazy_results_host_class(tree):
+    """Lazy_Results=true: statistics, scoring and the selected pose come from the GPU; the stacked end points are copied back only when
+    asked for, and are then the golden ones."""
+    g = np.load(os.path.join(GOLD, "oracle_seed0_h100_prune.npz"))
+    s = HostSolver(tree, "Num_Of_GPUs=1;Lazy_Results=true")
+    r0 = s.round(fetch=False)
+    assert np.array_equal(r0["per"].astype(np.int32), g["counts"]) and r0["selected_path"] == 104 and r0["selected_support"] == [5117, 5117]
+    assert r0["pose_found"] == 1 and max(r0["residuals"][:2]) < 0.1
+    r1 = s.round(fetch=True)
+    s.close()
+    assert np.array_equal(np.packbits(r1["conv"]), g["converged_bits"]) and np.array_equal(np.packbits(r1["inf"]), g["infinity_bits"])
+    assert np.array_equal(r1["tracks"][104].view(np.uint64), g["track104_h0"].view(np.uint64))
+
+
 def test_device_scoring_is_pinned_to_the_reference_util(problem, ransac0, default_round):
     """(f2) hcb200_score_tracks against the REFERENCE's MVG helpers (magmaHC/util.hpp:29-209 through oracle/_ref/libref_cpuhc.so; golden
     tests/golden/ref_util_support.npz): same candidates, same selected pose, inlier counts identical on >= 34 of the 36 candidates and

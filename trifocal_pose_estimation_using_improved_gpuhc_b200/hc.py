@@ -24,7 +24,7 @@ _lib = None
 # every symbol include/hcb200.h declares
 ABI_SYMBOLS = ("hcb200_workspace_bytes", "hcb200_abi_version", "hcb200_track", "hcb200_track_abort",
                "hcb200_build_target_params", "hcb200_score_tracks", "hcb200_refine_tracks", "hcb200_kernel_info", "hcb200_ffma_probe",
-               "hcb200_error_string", "hcb200_make_pose_record", "hcb200_reduce_pose_records")
+               "hcb200_error_string", "hcb200_make_pose_record", "hcb200_reduce_pose_records", "hcb200_count_solutions")
 
 
 class HCB200Error(RuntimeError):
@@ -58,6 +58,8 @@ def load_library(path=None):
     lib.hcb200_score_tracks.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.hcb200_refine_tracks.restype = i32
     lib.hcb200_refine_tracks.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.hcb200_count_solutions.restype = i32
+    lib.hcb200_count_solutions.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.hcb200_make_pose_record.restype = i32
     lib.hcb200_make_pose_record.argtypes = [vp, vp, vp, vp, ctypes.c_longlong, i32, vp]
     lib.hcb200_reduce_pose_records.restype = i32
@@ -282,6 +284,18 @@ class Tracker:
                                               p(self.d_K), p(self.d_support), p(self.d_best), p(self.d_ws))
         _check(rc, "hcb200_score_tracks")
         self.launches += 2
+
+    def count_solutions_device(self, n_hyp):
+        """Per-hypothesis (converged, infinity, real) counts of the last round, computed on the device; returns int array [H,3]."""
+        torch = self.torch
+        d_counts = torch.zeros((n_hyp, 3), dtype=torch.int32, device=self.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            rc = self.lib.hcb200_count_solutions(self._stream(), n_hyp, p(self.d_tracks), p(self.d_conv), p(self.d_inf), p(d_counts))
+        _check(rc, "hcb200_count_solutions")
+        self.launches += 1
+        torch.cuda.synchronize(self.device)
+        return d_counts.cpu().numpy()
 
     def make_pose_record(self, path_offset, rank, abort=False):
         """Enqueue: best record of the last score / abort launch -> the 128-byte exchange record self.d_pose_record (float32 [32])."""

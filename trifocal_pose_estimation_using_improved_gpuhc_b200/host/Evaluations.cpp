@@ -87,6 +87,18 @@ void Evaluations::Evaluate_RANSAC_HC_Sols(complex32* tracks, bool* conv, bool* i
   Percentage_Of_Real_Sols = (float)Num_Of_Real_Sols / total;
 }
 
+void Evaluations::Set_RANSAC_HC_Sol_Counts(const unsigned* c, int n_hypotheses)
+{
+  for (int ri = 0; ri < n_hypotheses; ri++) {
+    Num_Of_Coverged_Sols += c[3 * ri]; Num_Of_Inf_Sols += c[3 * ri + 1]; Num_Of_Real_Sols += c[3 * ri + 2];
+    Per_Hypothesis_Counts.push_back({c[3 * ri], c[3 * ri + 1], c[3 * ri + 2]});
+  }
+  const float total = (float)(num_of_tracks * num_of_ransac_iters);
+  Percentage_Of_Convergence = (float)Num_Of_Coverged_Sols / total;
+  Percentage_Of_Inf_Sols = (float)Num_Of_Inf_Sols / total;
+  Percentage_Of_Real_Sols = (float)Num_Of_Real_Sols / total;
+}
+
 // Evaluations.cpp:184-233: a converged track is unique if no later track agrees with it in every variable to 1e-4
 void Evaluations::Find_Unique_Sols(complex32* tracks, bool* conv)
 {

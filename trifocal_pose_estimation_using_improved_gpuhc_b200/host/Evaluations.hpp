@@ -22,6 +22,8 @@ public:
   void Write_Converged_Sols(hcb200::complex32* h_HC_Track_Sols, bool* h_is_HC_Sol_Converge);
   void Evaluate_HC_Sols(hcb200::complex32* h_HC_Track_Sols, bool* h_is_HC_Sol_Converge, bool* h_is_HC_Sol_Infinity, int ransac_sample_offset);
   void Evaluate_RANSAC_HC_Sols(hcb200::complex32* h_HC_Track_Sols, bool* h_is_HC_Sol_Converge, bool* h_is_HC_Sol_Infinity);
+  // the same statistics from per-hypothesis (converged, infinity, real) counts that were reduced on the device (hcb200_count_solutions)
+  void Set_RANSAC_HC_Sol_Counts(const unsigned* counts_conv_inf_real, int n_hypotheses);
   void Find_Unique_Sols(hcb200::complex32* h_GPU_HC_Track_Sols, bool* h_is_GPU_HC_Sol_Converge);
 
   void Convert_Trifocal_Translation(hcb200::complex32* h_GPU_HC_Track_Sols);

@@ -60,6 +60,12 @@ GPU_HC_Solver::GPU_HC_Solver(YAML::Node cfg) : Problem_Setting_YAML_File(cfg)
   verbose                         = cfg.as_or<bool>("Verbose", true);
   device_scoring                  = cfg.as_or<bool>("Device_Scoring", true);
   refine_iterations               = cfg.as_or<int>("Refine_Iterations", 0);
+  device_statistics               = cfg.as_or<bool>("Device_Statistics", true);
+  // Lazy_Results: auto (default) | true | false.  When statistics and scoring run on the GPU the host needs 12 bytes per hypothesis and one
+  // 128-byte record per GPU; the 248 bytes per path of end points are then copied back only when somebody asks for them (Track_Sols(),
+  // Sol_Converge(), Sol_Infinity(), hcb200_solver_copy_results).  auto = lazy from 2048 hypotheses up.
+  const std::string lz            = cfg.as_or<std::string>("Lazy_Results", "auto");
+  lazy_results                    = device_statistics && device_scoring && ((lz == "true") || (lz == "auto" && num_ransac_iters >= 2048));
   const std::string dtp           = cfg.as_or<std::string>("Device_Target_Params", "auto");
   device_target_params            = (dtp == "true") || (dtp == "auto" && num_ransac_iters >= 2048);
 
@@ -121,9 +127,8 @@ void GPU_HC_Solver::Allocate_Arrays()
   h_dHdx_Index = new int[dHdx_Index_Size];
   h_dHdt_Index = new int[dHdt_Index_Size];
   h_Camera_Intrinsic_Matrix = new float[9];
-  HC_CUDA(cudaMallocHost((void**)&h_GPU_HC_Track_Sols_Stack, sizeof(complex32) * n_paths * V1));
-  HC_CUDA(cudaMallocHost((void**)&h_is_GPU_HC_Sol_Converge_Stack, n_paths * sizeof(bool)));
-  HC_CUDA(cudaMallocHost((void**)&h_is_GPU_HC_Sol_Infinity_Stack, n_paths * sizeof(bool)));
+  const double t_alloc = wall_seconds();
+  (void)n_paths;                       // the stacked result arrays are pinned lazily (Allocate_Result_Stacks), while the GPUs track
   for (int g = 0; g < Num_Of_GPUs; g++) {
     DeviceShard& d = shard[g];
     const size_t H = sub_RANSAC_iters[g], paths = H * Num_Of_Tracks;
@@ -131,6 +136,8 @@ void GPU_HC_Solver::Allocate_Arrays()
     HC_CUDA(cudaMallocHost((void**)&h_Target_Params[g], sizeof(complex32) * P1 * (H ? H : 1)));
     HC_CUDA(cudaMallocHost((void**)&h_diffParams[g], sizeof(complex32) * P1 * (H ? H : 1)));
     HC_CUDA(cudaMallocHost((void**)&h_picked[g], sizeof(int) * 3 * (H ? H : 1)));
+    HC_CUDA(cudaMallocHost((void**)&h_counts[g], sizeof(unsigned) * 3 * (H ? H : 1)));
+    HC_CUDA(cudaMalloc((void**)&d.d_counts, sizeof(unsigned) * 3 * (H ? H : 1)));
     if (device_target_params) HC_CUDA(cudaMalloc((void**)&d.d_picked, sizeof(int) * 3 * (H ? H : 1)));
     HC_CUDA(cudaMalloc((void**)&d.d_start_sols, sizeof(complex32) * Num_Of_Tracks * V1));
     HC_CUDA(cudaMalloc((void**)&d.d_start_params, sizeof(complex32) * P1));
@@ -148,6 +155,42 @@ void GPU_HC_Solver::Allocate_Arrays()
     HC_CUDA(cudaMallocHost((void**)&h_score_best[g], sizeof(hcb200_best_record)));
   }
   arrays_allocated = true;
+  phase_seconds[0] = wall_seconds() - t_alloc;
+}
+
+// Lazy results: bring every end point and flag to the stacked host arrays now (all GPUs copy at the same time).
+void GPU_HC_Solver::Fetch_Results_To_Host()
+{
+  if (results_on_host) return;
+  DeviceGuard keep_callers_device;
+  Allocate_Result_Stacks();
+  const size_t V1 = Num_Of_Vars + 1;
+  for (int g = 0; g < Num_Of_GPUs; g++) {
+    DeviceShard& d = shard[g];
+    const size_t paths = (size_t)sub_RANSAC_iters[g] * Num_Of_Tracks;
+    if (!paths) continue;
+    cudaStream_t s = (cudaStream_t)d.stream;
+    HC_CUDA(cudaSetDevice(d.device));
+    HC_CUDA(cudaMemcpyAsync(h_GPU_HC_Track_Sols_Stack + (size_t)d.path_offset * V1, d.d_tracks, sizeof(complex32) * V1 * paths, cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaMemcpyAsync(h_is_GPU_HC_Sol_Converge_Stack + d.path_offset, d.d_conv, paths, cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaMemcpyAsync(h_is_GPU_HC_Sol_Infinity_Stack + d.path_offset, d.d_inf, paths, cudaMemcpyDeviceToHost, s));
+  }
+  for (int g = 0; g < Num_Of_GPUs; g++) {
+    if (!sub_RANSAC_iters[g]) continue;
+    HC_CUDA(cudaSetDevice(shard[g].device));
+    HC_CUDA(cudaStreamSynchronize((cudaStream_t)shard[g].stream));
+  }
+  results_on_host = true;
+}
+
+void GPU_HC_Solver::Allocate_Result_Stacks()
+{
+  if (result_stacks_allocated) return;
+  const size_t V1 = Num_Of_Vars + 1, n_paths = (size_t)Num_Of_Paths();
+  HC_CUDA(cudaMallocHost((void**)&h_GPU_HC_Track_Sols_Stack, sizeof(complex32) * n_paths * V1));
+  HC_CUDA(cudaMallocHost((void**)&h_is_GPU_HC_Sol_Converge_Stack, n_paths * sizeof(bool)));
+  HC_CUDA(cudaMallocHost((void**)&h_is_GPU_HC_Sol_Infinity_Stack, n_paths * sizeof(bool)));
+  result_stacks_allocated = true;
 }
 
 bool GPU_HC_Solver::Read_Problem_Data()
@@ -292,6 +335,7 @@ void GPU_HC_Solver::Data_Transfer_From_Host_To_Device()
     HC_CUDA(cudaStreamSynchronize((cudaStream_t)shard[g].stream));
     transfer_h2d_time[g] = wall_seconds() - t0;
   }
+  phase_seconds[3] = wall_seconds() - t0;
 }
 
 // The reference pins its 152 KB index table in L2 here (GPU_HC_Solver.cpp:364-378).  There is no table any more: the
@@ -322,11 +366,13 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
     if (rc != 0) { std::fprintf(stderr, "[ERROR] tracker launch failed on GPU %d: %s\n", g, hcb200_error_string(rc)); std::exit(2); }
     HC_CUDA(cudaEventRecord((cudaEvent_t)d.ev_stop, (cudaStream_t)d.stream));
   }
+  if (!lazy_results) Allocate_Result_Stacks();          // first round only: pin the stacked host arrays while the GPUs are tracking
   for (int g = 0; g < Num_Of_GPUs; g++) {               // GPU_HC_Solver.cpp:440-444
     HC_CUDA(cudaSetDevice(shard[g].device));
     HC_CUDA(cudaStreamSynchronize((cudaStream_t)shard[g].stream));
   }
   multi_GPUs_time = wall_seconds() - multi_GPUs_time;
+  phase_seconds[4] = multi_GPUs_time;
 
   // optional polish of the converged end points (outside the reference's timed region; Evaluations::Find_Unique_Sols compares
   // end points at DUPLICATE_SOL_DIFF_TOL = 1e-4, which raw single-precision end points of the same root do not always meet)
@@ -353,9 +399,16 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
     float ms = 0.f;
     HC_CUDA(cudaEventElapsedTime(&ms, (cudaEvent_t)d.ev_start, (cudaEvent_t)d.ev_stop));
     gpu_time[g] = ms * 1e-3;
-    HC_CUDA(cudaMemcpyAsync(h_GPU_HC_Track_Sols_Stack + (size_t)d.path_offset * V1, d.d_tracks, sizeof(complex32) * V1 * paths, cudaMemcpyDeviceToHost, s));
-    HC_CUDA(cudaMemcpyAsync(h_is_GPU_HC_Sol_Converge_Stack + d.path_offset, d.d_conv, paths, cudaMemcpyDeviceToHost, s));
-    HC_CUDA(cudaMemcpyAsync(h_is_GPU_HC_Sol_Infinity_Stack + d.path_offset, d.d_inf, paths, cudaMemcpyDeviceToHost, s));
+    if (!lazy_results) {
+      HC_CUDA(cudaMemcpyAsync(h_GPU_HC_Track_Sols_Stack + (size_t)d.path_offset * V1, d.d_tracks, sizeof(complex32) * V1 * paths, cudaMemcpyDeviceToHost, s));
+      HC_CUDA(cudaMemcpyAsync(h_is_GPU_HC_Sol_Converge_Stack + d.path_offset, d.d_conv, paths, cudaMemcpyDeviceToHost, s));
+      HC_CUDA(cudaMemcpyAsync(h_is_GPU_HC_Sol_Infinity_Stack + d.path_offset, d.d_inf, paths, cudaMemcpyDeviceToHost, s));
+    }
+    if (device_statistics) {                            // per-hypothesis counts are reduced on the GPU while the tracks are in flight
+      const int rc = hcb200_count_solutions(d.stream, sub_RANSAC_iters[g], (const float*)d.d_tracks, (const uint8_t*)d.d_conv, (const uint8_t*)d.d_inf, d.d_counts);
+      if (rc != 0) { std::fprintf(stderr, "[ERROR] statistics launch failed on GPU %d: %s\n", g, hcb200_error_string(rc)); std::exit(2); }
+      HC_CUDA(cudaMemcpyAsync(h_counts[g], d.d_counts, sizeof(unsigned) * 3 * sub_RANSAC_iters[g], cudaMemcpyDeviceToHost, s));
+    }
     if (Abort_RANSAC_by_Good_Sol) {
       HC_CUDA(cudaMemcpyAsync(h_Found_Trifocal_Sols[g], d.d_found, sizeof(bool), cudaMemcpyDeviceToHost, s));
       HC_CUDA(cudaMemcpyAsync(h_Trifocal_Sols_Batch_Index[g], d.d_found_index, paths * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -368,6 +421,8 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
     HC_CUDA(cudaStreamSynchronize((cudaStream_t)shard[g].stream));
     transfer_d2h_time[g] = wall_seconds() - t0_d2h;
   }
+  phase_seconds[5] = wall_seconds() - t0_d2h;
+  results_on_host = !lazy_results;
 
   // tiny gather: the best record of every GPU, reduced on the host (smallest global path id wins)
   found_path_ids.clear();
@@ -393,8 +448,16 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
     std::printf("## Timings:\n - GPU Computation Time = %7.2f (ms)\n", multi_GPUs_time * 1000);
   }
 
-  Evaluate_GPUHC_Sols->Evaluate_RANSAC_HC_Sols(h_GPU_HC_Track_Sols_Stack, h_is_GPU_HC_Sol_Converge_Stack, h_is_GPU_HC_Sol_Infinity_Stack);
+  const double t_stat = wall_seconds();
+  if (device_statistics) {
+    for (int g = 0; g < Num_Of_GPUs; g++)
+      if (sub_RANSAC_iters[g]) Evaluate_GPUHC_Sols->Set_RANSAC_HC_Sol_Counts(h_counts[g], sub_RANSAC_iters[g]);
+  } else {
+    Fetch_Results_To_Host();
+    Evaluate_GPUHC_Sols->Evaluate_RANSAC_HC_Sols(h_GPU_HC_Track_Sols_Stack, h_is_GPU_HC_Sol_Converge_Stack, h_is_GPU_HC_Sol_Infinity_Stack);
+  }
   per_hypothesis_counts = Evaluate_GPUHC_Sols->Per_Hypothesis_Counts;
+  phase_seconds[6] = wall_seconds() - t_stat;
   if (verbose) {
     std::cout << "\n## Evaluation of GPU-HC Solutions: " << std::endl;
     std::cout << " - Number of Converged Solutions:       " << Evaluate_GPUHC_Sols->Num_Of_Coverged_Sols << std::endl;
@@ -407,6 +470,7 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
 
   selected_path = -1;
   selected_support = {0u, 0u};
+  const double t_score = wall_seconds();
   if (device_scoring) {
     // support counting + selection on every GPU (hcb200_score_tracks), then the tiny gather: one 64-byte record per GPU,
     // reduced on the host — largest min(support21, support31), lowest global path id on ties
@@ -435,10 +499,18 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
       }
     }
     found_pose = selected_path >= 0;
-    if (found_pose)
-      Evaluate_GPUHC_Sols->Set_Selected_Solution(h_GPU_HC_Track_Sols_Stack + (size_t)selected_path * V1, selected_path,
-                                                 selected_support[0], selected_support[1]);
+    if (found_pose) {
+      // the selected end point alone (248 bytes) comes from the GPU that owns it; the stacked arrays may still be on the devices
+      for (int g = 0; g < Num_Of_GPUs; g++) {
+        const int first = shard[g].path_offset, paths = sub_RANSAC_iters[g] * Num_Of_Tracks;
+        if (selected_path < first || selected_path >= first + paths) continue;
+        HC_CUDA(cudaSetDevice(shard[g].device));
+        HC_CUDA(cudaMemcpy(h_selected_track, shard[g].d_tracks + (size_t)(selected_path - first) * V1 * 2, sizeof(complex32) * V1, cudaMemcpyDeviceToHost));   // d_tracks counts floats
+      }
+      Evaluate_GPUHC_Sols->Set_Selected_Solution(h_selected_track, selected_path, selected_support[0], selected_support[1]);
+    }
   } else {
+    Fetch_Results_To_Host();
     Evaluate_GPUHC_Sols->Transform_GPUHC_Sols_to_Trifocal_Relative_Pose(h_GPU_HC_Track_Sols_Stack, h_is_GPU_HC_Sol_Converge_Stack, h_Camera_Intrinsic_Matrix);
     found_pose = Evaluate_GPUHC_Sols->get_Solution_with_Maximal_Support(Num_Of_Triplet_Edgels, h_Triplet_Edge_Locations, h_Triplet_Edge_Tangents, h_Camera_Intrinsic_Matrix);
     if (found_pose) {
@@ -446,6 +518,10 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
       selected_support = {Evaluate_GPUHC_Sols->Max_Num_Of_Reproj_Inliers_Views21, Evaluate_GPUHC_Sols->Max_Num_Of_Reproj_Inliers_Views31};
     }
   }
+  phase_seconds[7] = wall_seconds() - t_score;
+  if (verbose)
+    std::printf("## Phases (s): allocate %.3f, host->device %.3f, GPU tracking %.3f, device->host %.3f, statistics %.3f, scoring %.3f\n",
+                phase_seconds[0], phase_seconds[3], phase_seconds[4], phase_seconds[5], phase_seconds[6], phase_seconds[7]);
   pose_residuals = {100.f, 100.f, 100.f, 100.f};
   if (found_pose) {
     Evaluate_GPUHC_Sols->Measure_Relative_Pose_Error(h_Camera_Pose21, h_Camera_Pose31);
@@ -510,7 +586,8 @@ GPU_HC_Solver::~GPU_HC_Solver()
       cudaFree(d.d_start_sols); cudaFree(d.d_start_params); cudaFree(d.d_target); cudaFree(d.d_diff); cudaFree(d.d_tracks);
       cudaFree(d.d_conv); cudaFree(d.d_inf); cudaFree(d.d_ws); cudaFree(d.d_support); cudaFree(d.d_score_best); cudaFree(d.d_refine_sums);
       cudaFreeHost(h_Target_Params[g]); cudaFreeHost(h_diffParams[g]); cudaFreeHost(h_score_best[g]); cudaFreeHost(h_picked[g]);
-      cudaFree(d.d_picked);
+      cudaFreeHost(h_counts[g]);
+      cudaFree(d.d_picked); cudaFree(d.d_counts);
     }
     cudaEventDestroy((cudaEvent_t)d.ev_start); cudaEventDestroy((cudaEvent_t)d.ev_stop);
     cudaStreamDestroy((cudaStream_t)d.stream);
@@ -518,6 +595,6 @@ GPU_HC_Solver::~GPU_HC_Solver()
   if (arrays_allocated) {
     std::free(h_Start_Sols); std::free(h_Start_Params);
     delete[] h_dHdx_Index; delete[] h_dHdt_Index; delete[] h_Camera_Intrinsic_Matrix;
-    cudaFreeHost(h_GPU_HC_Track_Sols_Stack); cudaFreeHost(h_is_GPU_HC_Sol_Converge_Stack); cudaFreeHost(h_is_GPU_HC_Sol_Infinity_Stack);
+    if (result_stacks_allocated) { cudaFreeHost(h_GPU_HC_Track_Sols_Stack); cudaFreeHost(h_is_GPU_HC_Sol_Converge_Stack); cudaFreeHost(h_is_GPU_HC_Sol_Infinity_Stack); }
   }
 }

@@ -56,9 +56,10 @@ public:
   // ---- additions for tests / benchmarks / callers that want the raw results --------------------------------
   int Num_Of_RANSAC_Iterations() const { return num_ransac_iters; }
   int Num_Of_Paths() const { return num_ransac_iters * Num_Of_Tracks; }
-  const hcb200::complex32* Track_Sols() const { return h_GPU_HC_Track_Sols_Stack; }     // [H*312][31]
-  const bool* Sol_Converge() const { return h_is_GPU_HC_Sol_Converge_Stack; }
-  const bool* Sol_Infinity() const { return h_is_GPU_HC_Sol_Infinity_Stack; }
+  const hcb200::complex32* Track_Sols() { Fetch_Results_To_Host(); return h_GPU_HC_Track_Sols_Stack; }     // [H*312][31]
+  const bool* Sol_Converge() { Fetch_Results_To_Host(); return h_is_GPU_HC_Sol_Converge_Stack; }
+  const bool* Sol_Infinity() { Fetch_Results_To_Host(); return h_is_GPU_HC_Sol_Infinity_Stack; }
+  void Fetch_Results_To_Host();      // Lazy_Results: copy every end point and flag back now (no-op when they already are on the host)
   const hcb200::complex32* Target_Params(int gpu_id) { Fetch_Target_Params_To_Host(); return h_Target_Params[gpu_id]; }
   void Fetch_Target_Params_To_Host();    // device-side Prepare_Target_Params: bring the parameters back when the host asks for them
   const int* Picked_Edgels(int gpu_id) const { return h_picked[gpu_id]; }     // [H_g][3] edgel indices drawn by the rand() stream
@@ -84,6 +85,7 @@ private:
     float *d_edgels = nullptr, *d_K = nullptr;
     float* d_tangents = nullptr;       // device-side Prepare_Target_Params: edgel tangents and the picked edgel triplets of this shard
     int* d_picked = nullptr;
+    unsigned* d_counts = nullptr;      // per-hypothesis (converged, infinity, real)
     int* d_found_index = nullptr;
     hcb200_best_record* d_best = nullptr;
     int* d_support = nullptr;                 // [paths][2] inlier supports from hcb200_score_tracks
@@ -137,6 +139,18 @@ private:
   bool device_target_params = false;
   bool target_params_on_host = true;     // h_Target_Params / h_diffParams hold this round's values
   int* h_picked[MAX_NUM_OF_GPUS] = {nullptr};
+  // Round statistics on the device (hcb200_count_solutions; YAML key Device_Statistics, default true): 12 bytes per hypothesis come
+  // back instead of the host walking every end point.  The stacked pinned result arrays are allocated lazily, AFTER the tracker
+  // launches, so that pinning gigabytes of host memory overlaps the GPU work instead of preceding it.
+  bool device_statistics = true;
+  bool result_stacks_allocated = false;
+  bool lazy_results = false, results_on_host = false;
+  hcb200::complex32 h_selected_track[32];
+  unsigned* h_counts[MAX_NUM_OF_GPUS] = {nullptr};
+  void Allocate_Result_Stacks();
+public:
+  double phase_seconds[8] = {0};     // allocate, read, prepare, h2d, solve, d2h, statistics, scoring (last round)
+private:
   int device_edgel_capacity = 0;
 
   std::vector<std::array<unsigned, 3>> per_hypothesis_counts;

@@ -3,6 +3,7 @@
 // It runs the GPU solver only: the reference's CPU-HC half is its baseline, not part of this product (no CPU fallback).
 // Files written under <root>/Output_Write_Files/: GPU_Timings.txt (ms per round), GPU_Sols_Statistics.txt
 // (converged <TAB> real <TAB> infinity per round) — SURVEY.md App. A.4.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -21,23 +22,36 @@ static void print_help()
               "  -s, --set KEY=VALUE   override one settings key (repeatable)\n");
 }
 
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static bool run_GPU_HC_Solver(YAML::Node settings, const std::string& root)
 {
   std::vector<double> all_ms;
+  double t[8];
+  t[0] = now_s();
   GPU_HC_Solver GPU_HC_(settings);
+  t[1] = now_s();
   GPU_HC_.Allocate_Arrays();
+  t[2] = now_s();
   for (int ti = 0; ti < TEST_RANSAC_TIMES; ti++) {
     if (!GPU_HC_.Read_Problem_Data()) return false;
     if (!GPU_HC_.Read_RANSAC_Data(ti)) return false;
+    t[3] = now_s();
     GPU_HC_.Prepare_Target_Params(ti);
     GPU_HC_.Set_RANSAC_Abort_Arrays();
+    t[4] = now_s();
     GPU_HC_.Data_Transfer_From_Host_To_Device();
     GPU_HC_.Set_CUDA_Stream_Attributes();
+    t[5] = now_s();
     GPU_HC_.Solve_by_GPU_HC();
+    t[6] = now_s();
     GPU_HC_.Free_Triplet_Edgels_Mem();
     GPU_HC_.Free_Arrays_for_Aborting_RANSAC();
     all_ms.push_back(GPU_HC_.multi_GPUs_time * 1000);
   }
+  t[7] = now_s();
+  std::printf("## Driver wall clock (s): solver object + CUDA context %.3f, allocate %.3f, read files %.3f, sample hypotheses %.3f, host->device %.3f, "
+              "solve + evaluate %.3f, free round %.3f\n", t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6]);
   double avg = 0, mx = 0, mn = 1e30, var = 0;
   for (double v : all_ms) { avg += v; mx = std::max(mx, v); mn = std::min(mn, v); }
   avg /= all_ms.size();
