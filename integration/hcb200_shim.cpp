@@ -28,13 +28,21 @@ void* workspace()
 }
 
 // d_startSols_array[0] / d_Track_array[0] are the bases of the contiguous buffers the pointer arrays were built from
-// (magma_cset_pointer, GPU_HC_Solver.cpp:352-353): read them back once, on the launch stream so the read is ordered after it.
+// (magma_cset_pointer, GPU_HC_Solver.cpp:352-353).  The base of a pointer array is read back ONCE — the reference builds each array a
+// single time from a buffer it never re-allocates (GPU_HC_Solver.cpp:137-184, 352-353) — and cached, so that later launches only
+// enqueue work and return, as the reference's wrappers do.  A host layer that re-points an array must call hcb200_shim_forget().
+struct BaseCache { const void* array; void* base; };
+BaseCache g_bases[32] = {};
 template <class T>
 T* first_entry(T** d_pointer_array, cudaStream_t s)
 {
+  for (const BaseCache& c : g_bases)
+    if (c.array == (const void*)d_pointer_array && c.base) return (T*)c.base;
   T* p = nullptr;
-  cudaMemcpyAsync(&p, d_pointer_array, sizeof p, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(&p, d_pointer_array, sizeof p, cudaMemcpyDeviceToHost, s);      // on the launch stream: ordered after the kernel that fills the array
   cudaStreamSynchronize(s);
+  for (BaseCache& c : g_bases)
+    if (!c.array) { c.array = (const void*)d_pointer_array; c.base = (void*)p; break; }
   return p;
 }
 
@@ -125,3 +133,6 @@ real_Double_t kernel_GPUHC_trifocal_2op1p_30x30_PH_CodeOpt_TrunPaths_TrunRANSAC_
                      d_Triplet_Edge_Locations, d_Intrinsic_Matrix, d_is_GPU_HC_Sol_Converge, d_is_GPU_HC_Sol_Infinity,
                      d_Found_Trifocal_Sols, d_Trifocal_Sols_Batch_Index);
 }
+
+// forget the cached pointer-array bases (only needed by a host layer that re-points d_startSols_array / d_Track_array)
+extern "C" void hcb200_shim_forget() { for (auto& c : g_bases) c = BaseCache{}; }

@@ -74,6 +74,26 @@ def test_batch_position_invariance_and_determinism_1000_hypotheses(problem, defa
     assert _digest(tr1[9 * 31200 + 312 * 57: 9 * 31200 + 312 * 58]) == str(g["digests"][57])
 
 
+@pytest.mark.parametrize("dataset,seed,prune", [(1, 3, True), (2, 5, False), (3, 11, True)])
+def test_other_datasets_and_sampler_seeds_bit_exact(problem, oracle, dataset, seed, prune):
+    """Inputs the committed goldens do not cover (they are all dataset 000 / sampler seed 0): other dataset files, other rand() streams,
+    both pruning modes — 40 hypotheses each, tracked by the oracle on the box's CPU and compared bit for bit (flags, counters, end points).
+    The one-off run over 1 872 000 such paths is profiles/parity_extended_r1.txt (tests/parity_extended.py)."""
+    rs = fixtures.load_ransac(dataset)
+    H = 40
+    picked = hc.sample_hypotheses(seed, H, rs["locations"].shape[0])
+    target, diff = hc.target_params_from_picks(picked, rs["locations"], rs["tangents"], problem["start_params"])
+    tr_o, cv_o, inf_o, st_o = oracle.track(target, diff, prune)
+    trk = hc.Tracker(problem=problem, stats=True)
+    trk.upload_params(target, diff)
+    trk.track(H, prune=prune)
+    tr, cv, inf, st = trk.results(H)
+    assert np.array_equal(cv, cv_o) and np.array_equal(inf, inf_o)
+    assert np.array_equal(st[:, :3], st_o[:, :3]) and np.array_equal(st[:, 3] & 0xffff, st_o[:, 3]) and np.array_equal(st[:, 3] >> 16, st_o[:, 4])
+    a, b = np.ascontiguousarray(tr[:, :30]), np.ascontiguousarray(tr_o[:, :30])
+    assert bool(np.all((a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))))
+
+
 def test_edge_cases_empty_and_invalid(problem):
     import torch
     trk = hc.Tracker(problem=problem)
@@ -235,10 +255,12 @@ def test_against_reference_gpu_kernels(problem, ransac0, default_round):
     trk.track(H, prune=True)
     tr, cv, inf, _ = trk.results(H)
     mine, theirs = hc.count_solutions(tr, cv, inf, H), hc.count_solutions(tr_r, cv_r, inf_r, H)
-    assert np.abs(mine[:, 0] - theirs[:, 0]).max() <= 6 and np.abs(mine[:, 0] - theirs[:, 0]).mean() <= 2.0
-    assert abs(int(mine[:, 0].sum()) - int(theirs[:, 0].sum())) <= 0.03 * theirs[:, 0].sum()
-    assert np.abs(mine[:, 2] - theirs[:, 2]).max() <= 2
-    assert (cv == cv_r).mean() > 0.98
+    # gates at 1.5x what is observed on these 30 hypotheses (|d converged| max 3, mean 0.6, totals 764 vs 770, real max 0, flags 99.70 %);
+    # the per-path statement — every difference is an unstable path — is tests/test_parity_envelope.py
+    assert np.abs(mine[:, 0] - theirs[:, 0]).max() <= 4 and np.abs(mine[:, 0] - theirs[:, 0]).mean() <= 0.9
+    assert abs(int(mine[:, 0].sum()) - int(theirs[:, 0].sum())) <= 0.012 * theirs[:, 0].sum()
+    assert np.abs(mine[:, 2] - theirs[:, 2]).max() <= 1
+    assert (cv == cv_r).mean() > 0.9955
     assert cv[104] == 1 and cv_r[104] == 1
     rel = np.abs(tr[104, :30] - tr_r[104, :30]).max() / np.abs(tr_r[104, :30]).max()
     assert rel < 1e-3

@@ -136,11 +136,12 @@ def test_tracker_vs_reference_cpuhc_first6(oracle, first6):
     g, tgt, tr, cv, inf, st = first6
     mine = hc.count_solutions(tr, cv, inf, 6)
     ref = np.array(REF_C3_FIRST6)
-    assert np.abs(mine[:, 0] - ref[:, 0]).max() <= 5          # converged per hypothesis
-    assert np.abs(mine[:, 1] - ref[:, 1]).max() <= 5          # infinity flags
+    # gates at 1.5x what is observed: |d| max 4 / 2 / 1 per hypothesis, totals 663 vs 666, flags 99.09 % / 99.52 % equal
+    assert np.abs(mine[:, 0] - ref[:, 0]).max() <= 6          # converged per hypothesis
+    assert np.abs(mine[:, 1] - ref[:, 1]).max() <= 3          # infinity flags
     assert np.abs(mine[:, 2] - ref[:, 2]).max() <= 2          # real solutions
-    assert abs(int(mine[:, 0].sum()) - int(ref[:, 0].sum())) <= 0.02 * ref[:, 0].sum()
-    assert (cv == g["converged"]).mean() > 0.97 and (inf == g["infinity"]).mean() > 0.97
+    assert abs(int(mine[:, 0].sum()) - int(ref[:, 0].sum())) <= 0.007 * ref[:, 0].sum()
+    assert (cv == g["converged"]).mean() > 0.986 and (inf == g["infinity"]).mean() > 0.992
 
 
 def test_endpoints_agree_after_newton_refinement(oracle, first6):
@@ -216,10 +217,13 @@ def test_full_default_run_goldens_agree_with_reference_totals():
     oc, rc = o["counts"], r["counts"]
     assert rc.sum(0).tolist() == [11088, 6590, 514]            # SURVEY.md App. C.2 (this toolchain's LAPACK)
     tot_o, tot_r = oc.sum(0), rc.sum(0)
-    assert abs(tot_o[0] - tot_r[0]) <= 0.01 * tot_r[0]         # converged
-    assert abs(tot_o[1] - tot_r[1]) <= 0.01 * tot_r[1]         # infinity
-    assert abs(tot_o[2] - tot_r[2]) <= 0.06 * tot_r[2]         # real (|imag| <= 1e-4 is the most fragile gate)
-    assert abs(tot_o[0] - 11098) <= 0.01 * 11098               # the authors' own CPU run
-    assert np.abs(oc[:, 0] - rc[:, 0]).max() <= 8 and np.abs(oc[:, 0] - rc[:, 0]).mean() < 2.5
+    # gates at 1.5x what is observed (oracle 11117 / 6574 / 509 vs reference 11088 / 6590 / 514: 0.26 %, 0.24 %, 1.0 %; per hypothesis
+    # |d converged| max 4, mean 1.35; 98.98 % of the converged flags equal).  The per-path statement — every difference is an unstable path —
+    # is tests/test_parity_envelope.py::test_differences_from_the_reference_cpu_are_unstable_paths_pruning_off
+    assert abs(tot_o[0] - tot_r[0]) <= 0.004 * tot_r[0]        # converged
+    assert abs(tot_o[1] - tot_r[1]) <= 0.004 * tot_r[1]        # infinity
+    assert abs(tot_o[2] - tot_r[2]) <= 0.015 * tot_r[2]        # real (|imag| <= 1e-4 is the most fragile gate)
+    assert abs(tot_o[0] - 11098) <= 0.003 * 11098              # the authors' own CPU run
+    assert np.abs(oc[:, 0] - rc[:, 0]).max() <= 6 and np.abs(oc[:, 0] - rc[:, 0]).mean() < 2.0
     same = (np.unpackbits(o["converged_bits"])[:31200] == np.unpackbits(r["converged_bits"])[:31200]).mean()
-    assert same > 0.975
+    assert same > 0.985
