@@ -117,6 +117,22 @@ def test_differences_from_the_pruned_reference_cpu_are_unstable_paths():
     _check(diff, unstable, "reference CPU-HC + pruning", max_outside=MAX_OUTSIDE["cpu_prune"], min_coverage=0.95)
 
 
+@pytest.mark.parametrize("H,key", [(100, "gpu_h100"), (1000, "gpu_h1000")])
+def test_differences_from_the_committed_reference_gpu_flags_are_unstable_paths(H, key):
+    """… vs the flags the UNMODIFIED reference GPU-HC++ kernels produced on a B200 (tests/golden/ref_gpuhc_*.npz, made by
+    tools/dump_ref_gpu.py + tools/parity_envelope_report.py --import-dumps); the `-m gpu` test below repeats this with the kernels run live."""
+    e = _load_env("envelope_seed0_h%d_prune.npz" % H)
+    r = np.load(os.path.join(GOLD, "ref_gpuhc_seed0_h%d.npz" % H))
+    P = H * 312
+    assert np.array_equal(e["picked"], r["picked"]) and bool(r["deterministic"][0])
+    assert np.array_equal(e["spec_conv"], r["our_converged_bits"]) and np.array_equal(e["spec_inf"], r["our_infinity_bits"])     # the GPU run WAS the spec
+    unstable = _bits(e["unstable"], P)
+    diff = (_bits(e["spec_conv"], P) != _bits(r["converged_bits"], P)) | (_bits(e["spec_inf"], P) != _bits(r["infinity_bits"], P)) | \
+           (_bits(e["spec_real"], P) != _bits(r["real_bits"], P))
+    _check(diff, unstable, "reference GPU-HC++ kernels (committed flags), %d hypotheses" % H, max_outside=MAX_OUTSIDE[key],
+           min_coverage=0.95 if H == 100 else 0.80)
+
+
 # observed stragglers (paths that differ from a reference implementation but flip in none of the variants), with 1.5x head-room
 MAX_OUTSIDE = {"gpu_h100": 3, "gpu_h1000": 60, "cpu_noprune": 6, "cpu_prune": 2}     # observed: 2, (see profiles), 4, 1
 

@@ -39,17 +39,54 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 sys.path.insert(0, os.path.dirname(PKG))
 
-N = 30          # variables / equations
-P_PAD = 33      # parameter index that holds the constant 1
-X_PAD = 30      # variable index that holds the constant 1
+N = 30          # variables / equations                        } of the problem being compiled: set by configure()
+P_PAD = 33      # parameter index that holds the constant 1    } (defaults: trifocal_2op1p_30x30)
+X_PAD = 30      # variable index that holds the constant 1     }
 WARP = 32
+SPEC = dict(name="trifocal_2op1p_30x30", n_vars=30, n_params=33, n_tracks=312, hx_terms=8, hx_parts=5, ht_terms=16, ht_parts=6,
+            n_depths=8, trifocal=1)
+
+
+def configure(spec):
+    """Select the minimal problem to compile (sizes as in gpuhc_settings.yaml: Num_Of_Vars, Num_Of_Params, Num_Of_Tracks,
+    dHdx_Max_Terms, dHdx_Max_Parts, dHdt_Max_Terms, dHdt_Max_Parts).  The lane-per-row mapping needs Num_Of_Vars <= 31."""
+    global N, P_PAD, X_PAD, SPEC
+    SPEC = dict(spec)
+    N, P_PAD, X_PAD = SPEC["n_vars"], SPEC["n_params"], SPEC["n_vars"]
+    assert 1 <= N <= 31 and SPEC["hx_parts"] == 5 and SPEC["ht_parts"] == 6
+
+
+def read_problem_dir(path):
+    """A problem folder in the reference's layout (problems/<name>/: gpuhc_settings.yaml, dHdx_indx.txt, dHdt_indx.txt;
+    reference Data_Reader.cpp:123-189, gpuhc_settings.yaml:5-34) -> (spec, dHdx index array, dHdt index array)."""
+    cfg = {}
+    for line in open(os.path.join(path, "gpuhc_settings.yaml")):
+        line = line.split("#")[0]
+        if ":" in line:
+            k, v = line.split(":", 1)
+            cfg[k.strip()] = v.strip().strip('"')
+    spec = dict(name=cfg["problem_name"], n_vars=int(cfg["Num_Of_Vars"]), n_params=int(cfg["Num_Of_Params"]), n_tracks=int(cfg["Num_Of_Tracks"]),
+                hx_terms=int(cfg["dHdx_Max_Terms"]), hx_parts=int(cfg["dHdx_Max_Parts"]), ht_terms=int(cfg["dHdt_Max_Terms"]),
+                ht_parts=int(cfg["dHdt_Max_Parts"]), n_depths=int(cfg.get("Num_Of_Depth_Vars", 0)), trifocal=int(cfg["problem_name"] == "trifocal_2op1p_30x30"))
+    if spec["trifocal"]:
+        spec["n_depths"] = 8
+    hx = np.array(open(os.path.join(path, "dHdx_indx.txt")).read().split(), dtype=np.int64)
+    ht = np.array(open(os.path.join(path, "dHdt_indx.txt")).read().split(), dtype=np.int64)
+    return spec, hx, ht
+
+
+_TABLES = None      # (dHdx, dHdt) flat index arrays of the configured problem; None = the packaged trifocal fixture
 
 
 def load_tables():
-    from trifocal_pose_estimation_using_improved_gpuhc_b200 import fixtures
-    prob = fixtures.load_problem()
-    hx = prob["dHdx_indx"].reshape(N, 8, 5, N)    # [col][term][part][row]   (Data_Reader.cpp:123-165 token order)
-    ht = prob["dHdt_indx"].reshape(16, 6, N)      # [term][part][row]
+    if _TABLES is None:
+        from trifocal_pose_estimation_using_improved_gpuhc_b200 import fixtures
+        prob = fixtures.load_problem()
+        hx_flat, ht_flat = prob["dHdx_indx"], prob["dHdt_indx"]
+    else:
+        hx_flat, ht_flat = _TABLES
+    hx = np.asarray(hx_flat).reshape(N, SPEC["hx_terms"], SPEC["hx_parts"], N)    # [col][term][part][row]   (Data_Reader.cpp:123-165 token order)
+    ht = np.asarray(ht_flat).reshape(SPEC["ht_terms"], SPEC["ht_parts"], N)       # [term][part][row]
     return hx, ht
 
 
