@@ -21,6 +21,19 @@ $(LIBDIR)/libhcb200.so: $(CSRC)/hc_tracker.cu $(CSRC)/hc_problem_gen.h include/h
 	mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(CSRC)/hc_tracker.cu 2> $(LIBDIR)/ptxas_hc_tracker.log || (cat $(LIBDIR)/ptxas_hc_tracker.log; false)
 
+# A library for ANOTHER minimal problem: the problem compiler turns a folder in the reference's layout into a header,
+# and the same tracker source is built against it.    make problem PROBLEM_DIR=problems/coupled_quadrics_8x8
+PROBLEM_DIR  ?= problems/coupled_quadrics_8x8
+PROBLEM_NAME := $(notdir $(patsubst %/,%,$(PROBLEM_DIR)))
+.PHONY: problem
+problem: $(LIBDIR)/libhcb200_$(PROBLEM_NAME).so
+$(CSRC)/hc_problem_gen_$(PROBLEM_NAME).h: $(PKG)/codegen/gen_eval.py $(PROBLEM_DIR)/dHdx_indx.txt $(PROBLEM_DIR)/dHdt_indx.txt $(PROBLEM_DIR)/gpuhc_settings.yaml
+	python $(PKG)/codegen/gen_eval.py --problem-dir $(PROBLEM_DIR) --out $@
+$(LIBDIR)/libhcb200_$(PROBLEM_NAME).so: $(CSRC)/hc_tracker.cu $(CSRC)/hc_problem_gen_$(PROBLEM_NAME).h include/hcb200.h
+	mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -DHC_PROBLEM_HEADER='"hc_problem_gen_$(PROBLEM_NAME).h"' -shared -o $@ $(CSRC)/hc_tracker.cu \
+	  2> $(LIBDIR)/ptxas_hc_tracker_$(PROBLEM_NAME).log || (cat $(LIBDIR)/ptxas_hc_tracker_$(PROBLEM_NAME).log; false)
+
 HOST_SRCS := $(HOST)/GPU_HC_Solver.cpp $(HOST)/Data_Reader.cpp $(HOST)/Evaluations.cpp $(HOST)/host_capi.cpp
 HOST_HDRS := $(wildcard $(HOST)/*.hpp) include/hcb200.h
 $(LIBDIR)/libhcb200_host.so: $(HOST_SRCS) $(HOST_HDRS) $(LIBDIR)/libhcb200.so

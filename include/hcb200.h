@@ -34,7 +34,7 @@ extern "C" {
 #define HCB200_NUM_VARS 30
 #define HCB200_NUM_PARAMS 33
 #define HCB200_NUM_TRACKS 312
-#define HCB200_ABI_VERSION 2
+#define HCB200_ABI_VERSION 3
 
 /* flags */
 #define HCB200_FLAG_PRUNE_PATHS 1u   /* positive-depth path pruning (always on in the reference GPU kernels, …TrunPaths.cu:148-154) */
@@ -68,6 +68,13 @@ typedef struct {
 /* Device workspace the launches need (work counter + reduction scratch); zeroing is done by the launch itself. */
 size_t hcb200_workspace_bytes(void);
 int hcb200_abi_version(void);
+
+/* The minimal problem compiled into this library (the reference reads these from problems/<name>/gpuhc_settings.yaml:
+ * Num_Of_Vars, Num_Of_Params, Num_Of_Tracks, problem_name).  libhcb200.so is trifocal_2op1p_30x30 (30, 33, 312, 1); a library built by
+ * `make problem PROBLEM_DIR=…` for another problem folder reports that problem's sizes, takes arrays of those sizes in hcb200_track /
+ * hcb200_refine_tracks / hcb200_count_solutions, and answers cudaErrorNotSupported in the trifocal-only entry points (abort, scoring,
+ * pose records, target parameters from edgels).  Any pointer may be NULL.  Returns 0. */
+int hcb200_problem_info(int* n_vars, int* n_params, int* n_tracks, int* is_trifocal, const char** name);
 
 /* Replaces kernel_GPUHC_trifocal_2op1p_30x30_PH_CodeOpt_TrunPaths (…TrunPaths.cu:292-386).
  * Tracks all 312*n_hyp paths in one launch (0 <= n_hyp <= 3 441 480: path ids are 31-bit).  `stats` may be NULL.

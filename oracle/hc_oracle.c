@@ -476,7 +476,7 @@ void hco_track_path_v(const int* dHdx, const int* dHdt, const hco_c32* start_sol
     if (cfg->prune) {                                                                               /* :148-154 */
       if (check_depths) {
         int all_pos = 1;
-        for (int i = 0; i < 8; i++) all_pos &= (x[i].re > 0.0f);
+        for (int i = 0; i < HCO_NUM_DEPTHS; i++) all_pos &= (x[i].re > 0.0f);
         if (t0 > 0.0f) check_depths = all_pos ? 0 : 1;
       }
       if ((double)t0 > 0.95 && check_depths) { s.end_reason = 2; break; }
@@ -587,6 +587,7 @@ void hco_track_batch_v(const int* dHdx, const int* dHdt, const hco_c32* start_so
   }
 }
 
+#if HCO_TRIFOCAL   /* scoring and hypothesis generation know the meaning of the trifocal unknowns / parameters */
 /* ------------------------------------------------------------------------------------------------------------
  * early-abort scoring: dev-trifocal_2op1p-eval.cuh:28-250 with a fixed FMA placement; rnorm3df -> 1/sqrtf,
  * hypotf -> sqrtf (both correctly rounded here and, with -prec-sqrt/-prec-div, on the device). */
@@ -675,6 +676,7 @@ void hco_prepare_target_params(unsigned seed, int n_hyp, int n_edgels, const flo
   }
 }
 
+#endif   /* HCO_TRIFOCAL */
 /* ------------------------------------------------------------------------------------------------------------
  * double-precision Newton polish against the target system (test helper) */
 typedef struct { double re, im; } zc;

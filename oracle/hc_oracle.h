@@ -25,13 +25,29 @@
 extern "C" {
 #endif
 
+/* Problem sizes (gpuhc_settings.yaml: Num_Of_Vars, Num_Of_Params, Num_Of_Tracks, dHdx_Max_Terms, dHdt_Max_Terms).  Defaults: the
+ * trifocal problem; `make -C oracle problem_oracle PROBLEM_DIR=…` builds the same source for another problem folder with -D overrides. */
+#ifndef HCO_N
 #define HCO_N 30          /* variables == equations */
+#endif
+#ifndef HCO_NP
 #define HCO_NP 33         /* parameters (index 33 is the constant-one pad) */
+#endif
+#ifndef HCO_TRACKS
 #define HCO_TRACKS 312
+#endif
+#ifndef HCO_HX_TERMS
 #define HCO_HX_TERMS 8
+#endif
 #define HCO_HX_PARTS 5
+#ifndef HCO_HT_TERMS
 #define HCO_HT_TERMS 16
+#endif
 #define HCO_HT_PARTS 6
+#ifndef HCO_NUM_DEPTHS
+#define HCO_NUM_DEPTHS 8  /* leading unknowns tested by the positive-depth pruning (…TrunPaths.cu:148-154) */
+#endif
+#define HCO_TRIFOCAL (HCO_N == 30 && HCO_NP == 33)     /* pose scoring / target parameters from edgels exist for this problem only */
 
 typedef struct { float re, im; } hco_c32;
 

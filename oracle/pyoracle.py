@@ -53,15 +53,32 @@ def build_oracle(force=False):
     return ORACLE_SO
 
 
+def build_problem_oracle(problem_dir):
+    name = os.path.basename(os.path.normpath(problem_dir))
+    so = os.path.join(HERE, "liboracle_hc_%s.so" % name)
+    src = os.path.join(HERE, "hc_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "problem_oracle", "PROBLEM_DIR=" + os.path.abspath(problem_dir)], stdout=subprocess.DEVNULL)
+    return so
+
+
 class Oracle:
-    def __init__(self, problem):
-        build_oracle()
-        self.lib = ctypes.CDLL(ORACLE_SO)
+    def __init__(self, problem, problem_dir=None):
+        """problem: dict with start_sols, start_params, dHdx_indx, dHdt_indx.  problem_dir: a problem folder (reference layout) other than
+        the trifocal one — the same C source is built for its sizes (`make -C oracle problem_oracle`), problem["spec"] gives them."""
+        if problem_dir is None:
+            build_oracle()
+            self.lib = ctypes.CDLL(ORACLE_SO)
+            self.N, self.NP1, self.TRACKS = N, NP1, TRACKS
+        else:
+            self.lib = ctypes.CDLL(build_problem_oracle(problem_dir))
+            spec = problem["spec"]
+            self.N, self.NP1, self.TRACKS = spec["n_vars"], spec["n_params"] + 1, spec["n_tracks"]
         self.lib.hco_newton_refine_f64.restype = ctypes.c_double
         self.hx = np.ascontiguousarray(problem["dHdx_indx"], np.int32)
         self.ht = np.ascontiguousarray(problem["dHdt_indx"], np.int32)
-        ss = np.ones((TRACKS, N + 1), np.complex64)
-        ss[:, :N] = problem["start_sols"]
+        ss = np.ones((self.TRACKS, self.N + 1), np.complex64)
+        ss[:, :self.N] = problem["start_sols"]
         self.start_sols = ss
         self.start_params = np.concatenate([problem["start_params"], [1.0]]).astype(np.complex64)
         self._ss = c2f(ss)
@@ -69,22 +86,22 @@ class Oracle:
 
     # evaluators -------------------------------------------------------------------------------------------------
     def eval_Hx(self, x31, p34):
-        A = np.zeros((N, N, 2), np.float32)
+        A = np.zeros((self.N, self.N, 2), np.float32)
         self.lib.hco_eval_Hx(_vp(self.hx), _vp(c2f(x31)), _vp(c2f(p34)), _vp(A))
         return f2c(A)
 
     def eval_H(self, x31, p34):
-        b = np.zeros((N, 2), np.float32)
+        b = np.zeros((self.N, 2), np.float32)
         self.lib.hco_eval_H(_vp(self.ht), _vp(c2f(x31)), _vp(c2f(p34)), _vp(b))
         return f2c(b)
 
     def eval_Ht(self, x31, p34, dp34):
-        b = np.zeros((N, 2), np.float32)
+        b = np.zeros((self.N, 2), np.float32)
         self.lib.hco_eval_Ht(_vp(self.ht), _vp(c2f(x31)), _vp(c2f(p34)), _vp(c2f(dp34)), _vp(b))
         return f2c(b)
 
     def param_homotopy(self, t, target34):
-        p = np.zeros((NP1, 2), np.float32)
+        p = np.zeros((self.NP1, 2), np.float32)
         self.lib.hco_param_homotopy(ctypes.c_float(t), _vp(self._sp), _vp(c2f(target34)), _vp(p))
         return f2c(p)
 
@@ -96,8 +113,8 @@ class Oracle:
 
     # tracker ----------------------------------------------------------------------------------------------------
     def prepare_target_params(self, seed, n_hyp, locations, tangents):
-        tgt = np.zeros((n_hyp, NP1, 2), np.float32)
-        dif = np.zeros((n_hyp, NP1, 2), np.float32)
+        tgt = np.zeros((n_hyp, self.NP1, 2), np.float32)
+        dif = np.zeros((n_hyp, self.NP1, 2), np.float32)
         picked = np.zeros((n_hyp, 3), np.int32)
         loc = np.ascontiguousarray(locations, np.float32)
         tan = np.ascontiguousarray(tangents, np.float32)
@@ -109,8 +126,8 @@ class Oracle:
         """Returns tracks[P,31] c64, converged[P] u8, infinity[P] u8, stats[P,5] i32 (steps,pred,corr,rejected,reason).
         variant: dict of hco_variant fields (None == the arithmetic spec)."""
         n_hyp = target.shape[0]
-        P = n_hyp * TRACKS
-        tr = np.zeros((P, N + 1, 2), np.float32)
+        P = n_hyp * self.TRACKS
+        tr = np.zeros((P, self.N + 1, 2), np.float32)
         cv = np.zeros(P, np.uint8)
         inf = np.zeros(P, np.uint8)
         st = np.zeros((P, 5), np.int32)
@@ -136,7 +153,7 @@ class Oracle:
         return f2c(x), sd.value, sx.value
 
     def newton_refine(self, target34, x31, iters=6):
-        out = np.zeros((N, 2), np.float64)
+        out = np.zeros((self.N, 2), np.float64)
         res = self.lib.hco_newton_refine_f64(_vp(self.hx), _vp(self.ht), _vp(c2f(target34)), _vp(c2f(x31)), iters, _vp(out))
         return out[:, 0] + 1j * out[:, 1], res
 
@@ -164,6 +181,26 @@ class ReferenceCPU:
         if rc != 0:
             raise RuntimeError("ref_cpuhc_run failed with code %d" % rc)
         return f2c(tr), cv, inf, f2c(tp), sec.value
+
+    def run_problem(self, problem_dir, target, n_cores=None):
+        """The reference's generic CPU-HC on ANOTHER problem folder (reference layout); target: complex64 [H][Num_Of_Params + 1].
+        Returns tracks [H*T][N+1] c64, converged, infinity, seconds."""
+        import shutil
+        import tempfile
+        from trifocal_pose_estimation_using_improved_gpuhc_b200.codegen import gen_eval
+        spec = gen_eval.read_problem_dir(problem_dir)[0]
+        n_hyp, P = target.shape[0], target.shape[0] * spec["n_tracks"]
+        tr = np.zeros((P, spec["n_vars"] + 1, 2), np.float32)
+        cv, inf, sec = np.zeros(P, np.uint8), np.zeros(P, np.uint8), ctypes.c_double()
+        with tempfile.TemporaryDirectory() as tmp:
+            shutil.copytree(problem_dir, os.path.join(tmp, "problems", spec["name"]))
+            os.makedirs(os.path.join(tmp, "Output_Write_Files"))
+            os.makedirs(os.path.join(tmp, "build", "bin"))
+            rc = self.lib.ref_cpuhc_run_problem(os.path.join(tmp, "build", "bin").encode(), spec["name"].encode(), n_hyp, n_cores or (os.cpu_count() or 1),
+                                                _vp(c2f(target)), _vp(tr), _vp(cv), _vp(inf), ctypes.byref(sec))
+        if rc != 0:
+            raise RuntimeError("ref_cpuhc_run_problem failed with code %d" % rc)
+        return f2c(tr), cv, inf, sec.value
 
     def eval_Hx(self, hx, x31, p34):
         A = np.zeros((N * N, 2), np.float32)

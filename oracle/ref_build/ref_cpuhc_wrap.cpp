@@ -84,6 +84,51 @@ int ref_cpuhc_run(const char* bin_dir, int n_hyp, unsigned seed, int dataset_ind
   return rc;
 }
 
+// The same solver on ANOTHER problem folder (<tree>/problems/<problem_name>/ in the reference's layout): the reference's CPU-HC takes every size
+// from gpuhc_settings.yaml and its evaluators walk the index tables with run-time sizes, so it runs any problem given as data.  The RANSAC
+// front end (edgels -> target parameters) is trifocal-specific and is not used: the caller supplies the target parameters
+// (n_hyp * (Num_Of_Params + 1) complex, last entry of every hypothesis = 1).
+int ref_cpuhc_run_problem(const char* bin_dir, const char* problem_name, int n_hyp, int n_cores, const float* in_target_params,
+                          float* out_tracks, unsigned char* out_conv, unsigned char* out_inf, double* out_seconds)
+{
+  char cwd[4096];
+  if (!in_target_params || !problem_name) return 7;
+  if (!getcwd(cwd, sizeof cwd)) return 1;
+  if (chdir(bin_dir) != 0) return 2;
+  g_hcb200_ref_num_hyp = n_hyp;
+  int rc = 0;
+  try {
+    YAML::Node cfg = YAML::LoadFile(std::string("../../problems/") + problem_name + "/gpuhc_settings.yaml");
+    cfg.set("Num_Of_Cores", std::to_string(n_cores));
+    CPU_HC_Solver s(cfg);
+    s.Allocate_Arrays();
+    if (!s.Read_Problem_Data()) rc = 3;
+    if (!rc) {
+      const int P1 = s.Num_Of_Params + 1;
+      for (int i = 0; i < n_hyp * P1; i++) {
+        s.h_Target_Params[i] = MAGMA_C_MAKE(in_target_params[2 * i], in_target_params[2 * i + 1]);
+        s.h_diff_params[i]   = s.h_Target_Params[i] - s.h_Start_Params[i % P1];
+      }
+      s.Set_Initial_Array_Vals();
+      double t = s.CPUHC_Generic_Solver_Eval_by_Indx(n_cores, cpu_eval_indx_dHdX_trifocal_2op1p_30,
+                                                      cpu_eval_indx_dHdt_trifocal_2op1p_30,
+                                                      cpu_eval_indx_H_trifocal_2op1p_30);
+      if (out_seconds) *out_seconds = t;
+      const int n_paths = n_hyp * s.Num_Of_Tracks, V1 = s.Num_Of_Vars + 1;
+      if (out_tracks) std::memcpy(out_tracks, s.h_CPU_HC_Track_Sols, sizeof(magmaFloatComplex) * (size_t)n_paths * V1);
+      for (int i = 0; i < n_paths; i++) {
+        if (out_conv) out_conv[i] = s.h_is_Track_Converged[i] ? 1 : 0;
+        if (out_inf)  out_inf[i]  = s.h_is_Track_Inf_Failed[i] ? 1 : 0;
+      }
+    }
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "ref_cpuhc_run_problem: %s\n", e.what());
+    rc = 5;
+  }
+  if (chdir(cwd) != 0 && !rc) rc = 6;
+  return rc;
+}
+
 // The reference's three index-table evaluators (cpu-jacobian-evals/cpu-eval-indx_trifocal_2op1p_30x30.hpp:22-89),
 // exposed so the oracle's evaluators can be pinned term by term.  A is column-major 30x30 (LAPACK layout).
 void ref_eval_dHdX(const int* dHdx_index, const float* x31, const float* p34, float* A900)

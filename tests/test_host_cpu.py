@@ -27,7 +27,7 @@ def test_device_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libhcb200.so does not export " + n
     assert set(names) == set(hc.ABI_SYMBOLS)
-    assert lib.hcb200_abi_version() == 2
+    assert lib.hcb200_abi_version() == 3
     assert lib.hcb200_workspace_bytes() >= 16
 
 

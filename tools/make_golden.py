@@ -68,6 +68,36 @@ def main():
                                 real_bits=np.packbits(real), counts=counts.astype(np.int32), seconds=np.float64(sec), cores=np.int32(os.cpu_count()))
             print("refpruned100: %.1f s, totals conv/inf/real" % sec, counts.sum(0).tolist())
 
+    if "problem" in what:
+        # OTHER minimal problems (problems/<name>/, tools/make_synthetic_problem.py): the reference's own generic CPU-HC and the oracle built
+        # for each problem's sizes, on 16 hypotheses
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import make_synthetic_problem as msp
+        for name in msp.NAMES:
+            msp.select(name)
+            pdir = os.path.join(ROOT, "problems", name)
+            p2 = msp.load_folder(pdir)
+            n = p2["spec"]["n_vars"]
+            tgt = msp.target_params(16)
+            tr_r, cv_r, inf_r, sec = ref.run_problem(pdir, tgt)
+            o2 = Oracle(p2, problem_dir=pdir)
+            sp1 = np.concatenate([p2["start_params"], [1.0]]).astype(np.complex64)
+            dif = np.empty_like(tgt)
+            dif.real, dif.imag = tgt.real - sp1.real, tgt.imag - sp1.imag
+            out = dict(target=tgt, ref_tracks=tr_r[:, :n], ref_converged=np.packbits(cv_r), ref_infinity=np.packbits(inf_r))
+            for prune in (False, True):
+                tr, cv, inf, st = o2.track(tgt, dif, prune)
+                k = "prune" if prune else "noprune"
+                a = np.ascontiguousarray(tr[:, :n]).view(np.float32).copy()
+                a[np.isnan(a)] = np.float32(np.nan)
+                out.update({"oracle_converged_" + k: np.packbits(cv), "oracle_infinity_" + k: np.packbits(inf), "oracle_steps_" + k: st[:, 0].astype(np.uint8),
+                            "oracle_digest_" + k: np.array(hashlib.sha256(a.view(np.uint32).tobytes()).hexdigest())})
+                if not prune:
+                    out["oracle_tracks_h0"] = tr[:p2["spec"]["n_tracks"], :n]
+                print("problem %s, pruning %s: oracle converged %d infinity %d of %d | reference CPU-HC converged %d infinity %d (%.2f s)"
+                      % (name, prune, cv.sum(), inf.sum(), len(cv), cv_r.sum(), inf_r.sum(), sec))
+            np.savez_compressed(os.path.join(OUT, "problem_%s_h16.npz" % name), **out)
+
     if "refutil" in what:
         import ctypes
         from oracle.pyoracle import REF_CPU_SO, c2f

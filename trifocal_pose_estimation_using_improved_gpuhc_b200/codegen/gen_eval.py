@@ -146,7 +146,7 @@ def level_schedule(hx_terms, K1, segments, seg_cols):
                 busy[r] = lvl
             level_of_col[c] = lvl
             groups.append((lvl, g, c, part, u.copy()))
-    n_levels = 1 + max(l for l, *_ in groups)
+    n_levels = 1 + max([l for l, *_ in groups] or [-1])
     levels, first_shared = [], []
     for T in range(n_levels):
         here = [(g, c, part) for (l, g, c, part, u) in groups if l == T]
@@ -187,6 +187,15 @@ def schedule(seqs):
 
 
 def analyze_blocks(hx_terms):
+    """Block structure of the Jacobian, or (0, [], []) — no block-parallel phase, every pivot step warp-wide — when the rows do not
+    fall into independent groups of at most six (e.g. a small fully coupled system)."""
+    try:
+        return _analyze_blocks(hx_terms)
+    except AssertionError:
+        return 0, [], []
+
+
+def _analyze_blocks(hx_terms):
     """Symbolic elimination -> (K1, segments, seg_cols).  segments[g] = sorted rows (<= 6), seg_cols[g] = the segment's
     private pivot columns in natural order; columns K1..N-1 are dense (shared by all rows)."""
     P = np.zeros((N, N), bool)
@@ -219,7 +228,8 @@ def analyze_blocks(hx_terms):
     comps = {}
     for r in range(N):
         comps.setdefault(find(r), []).append(r)
-    comps = sorted(comps.values(), key=lambda rows: min(k for k in range(K1) if set(cand_of[k]) & set(rows)))
+    assert K1 > 0 and all(len(rows) <= 6 for rows in comps.values())
+    comps = sorted(comps.values(), key=lambda rows: min([k for k in range(K1) if set(cand_of[k]) & set(rows)] or [N]))
     # pack components into 6-row segments (first-fit in order of their first pivot column)
     segments = []
     for rows in comps:
@@ -320,11 +330,17 @@ def build():
     # ---- block structure -> lane permutation and register slots -------------------------------------------
     K1, segments, seg_cols = analyze_blocks(hx_terms)
     levels, level_of_col, sp_first_shared = level_schedule(hx_terms, K1, segments, seg_cols)
+    if len(levels) > 4 or (len(levels) + N - K1) % 2:      # the kernel packs at most four levels per lane word and moves slots in pairs
+        K1, segments, seg_cols = 0, [], []
+        levels, level_of_col, sp_first_shared = level_schedule(hx_terms, K1, segments, seg_cols)
     SEG = 6
     row_of_lane = [-1] * WARP
     for g, seg in enumerate(segments):
         for i, r in enumerate(seg):
             row_of_lane[g * SEG + i] = r
+    if not segments:                               # no block structure: row r on lane r
+        for r in range(N):
+            row_of_lane[r] = r
     lane_of_row = [row_of_lane.index(r) for r in range(N)]
     nsp = len(levels)
     nd = N - K1
@@ -409,6 +425,11 @@ def build():
 
     h_slots = sched_rows(h_terms, cq_index, False)
     ht_slots = sched_rows(h_terms, dq_index, True)
+    while len(ht_slots) < len(h_slots):            # H and Ht share one slot loop in the kernel: pad with empty slots (cq[0] == 0 times x[N] == 1)
+        ht_slots.append([None] * WARP)
+    assert (nsp + nd) % 2 == 0, "the kernel moves register slots in pairs: levels + dense columns must be even"
+    assert all(row_of_lane[l] >= 0 for l in range(N)) and all(row_of_lane[l] < 0 for l in range(N, WARP)), "rows must occupy lanes 0..N-1"
+    assert all(-2 <= c <= 5 for lst in list(hx_terms.values()) + list(h_terms.values()) for c, _, _, _ in lst), "coefficients are packed into 3 bits"
 
     # ---- bank-conflict-aware table layouts --------------------------------------------------------------------------
     hx_rows = [row for _, row in hx_slots]
@@ -504,11 +525,11 @@ def emit(g, path):
     L = []
     w = L.append
     w("// GENERATED by codegen/gen_eval.py from the problem's evaluation-index tables — do not edit.")
-    w("// Problem: trifocal_2op1p_30x30 (30 equations, 30 unknowns, 33 parameters, 312 paths).")
+    w("// Problem: %s (%d equations, %d unknowns, %d parameters, %d paths)." % (SPEC["name"], N, N, SPEC["n_params"], SPEC["n_tracks"]))
     w("#ifndef HC_PROBLEM_GEN_H")
     w("#define HC_PROBLEM_GEN_H")
     w("#define HCG_N %d" % N)
-    w("#define HCG_NUM_PARAMS 33")
+    w("#define HCG_NUM_PARAMS %d" % SPEC["n_params"])
     w("#define HCG_NUM_CQ %d   /* coef*p_a*p_b table (entry 0 == 0) */" % ncq)
     w("#define HCG_NUM_DQ %d   /* coef*(dp_a*p_b + dp_b*p_a) table (entry 0 == 0) */" % ndq)
     w("#define HCG_CQ_ROUNDS %d" % rounds(ncq))
@@ -577,9 +598,9 @@ def emit(g, path):
     w("#define HCG_ND %d        /* dense slots */" % g["nd"])
     w("#define HCG_NSLOT %d     /* register slots per row */" % g["nslot"])
     w("#define HCG_SEG 6")
-    w("#define HCG_NSEG %d" % len(g["segments"]))
+    w("#define HCG_NSEG %d" % max(1, len(g["segments"])))
     w("// per super-step: first register slot of the shared columns that can be non-zero in a participating row")
-    w("#define HCG_SP_FIRST_SHARED_SLOT_INIT { " + ",".join(str(g["nsp"] + c - g["K1"]) for c in g["sp_first_shared"]) + " }")
+    w("#define HCG_SP_FIRST_SHARED_SLOT_INIT { " + ",".join([str(g["nsp"] + c - g["K1"]) for c in g["sp_first_shared"]] or ["0"]) + " }")
     w("#define HCG_ROW_OF_LANE_INIT { " + ",".join(str(r) for r in g["row_of_lane"]) + " }")
     w("#define HCG_LANE_OF_ROW_INIT { " + ",".join(str(r) for r in g["lane_of_row"]) + " }")
     # per-lane info word: nz mask over slots (bits 0..nslot-1) | selector bits << 20
@@ -618,7 +639,12 @@ def emit(g, path):
     for t, (ca, cb, sb) in enumerate(g["scatter"]):
         w("  X(%d, %d, %d, %d) \\" % (t, ca, cb, sb))
     w("")
-
+    w("// problem identity: the kernel takes every size from this header (codegen/gen_eval.py --problem-dir compiles another problem)")
+    w("#define HCG_PROBLEM_NAME \"%s\"" % SPEC["name"])
+    w("#define HCG_TRACKS %d        /* homotopy paths per hypothesis (Num_Of_Tracks) */" % SPEC["n_tracks"])
+    w("#define HCG_NUM_DEPTHS %d      /* leading variables that are depths: positive-depth pruning tests them (0: no pruning) */" % SPEC["n_depths"])
+    w("#define HCG_TRIFOCAL %d        /* 1: the trifocal relative-pose problem (in-kernel scoring, pose records, target-parameter gather) */" % SPEC["trifocal"])
+    w("")
     w("#endif")
     text = "\n".join(L) + "\n"
     with open(path, "w") as f:
@@ -860,9 +886,34 @@ def emit_tp(g, t, path):
     return text
 
 
-def main():
+def compile_problem(problem_dir, out):
+    """Problem folder in the reference's layout -> generated header for csrc/hc_tracker.cu (-DHC_PROBLEM_HEADER)."""
+    global _TABLES
+    spec, hx, ht = read_problem_dir(problem_dir)
+    configure(spec)
+    _TABLES = (hx, ht)
     g = build()
-    out = os.path.join(PKG, "csrc", "hc_problem_gen.h")
+    emit(g, out)
+    return g
+
+
+def main():
+    import argparse
+    ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
+    ap.add_argument("--problem-dir", default=None, help="problems/<name>/ in the reference's layout (default: the packaged trifocal_2op1p_30x30 tables)")
+    ap.add_argument("--out", default=None, help="header to write (default: csrc/hc_problem_gen.h, or csrc/hc_problem_gen_<name>.h with --problem-dir)")
+    a = ap.parse_args()
+    if a.problem_dir:
+        spec = read_problem_dir(a.problem_dir)[0]
+        out = a.out or os.path.join(PKG, "csrc", "hc_problem_gen_%s.h" % spec["name"])
+        g = compile_problem(a.problem_dir, out)
+        print("problem %s: N %d, parameters %d, paths %d | K1 %d segments %s | classes %s | Hx slots %d, H slots %d, Ht slots %d | cq %d dq %d | pairs %d triples %d"
+              % (SPEC["name"], N, SPEC["n_params"], SPEC["n_tracks"], g["K1"], g["segments"], g["classes"], len(g["hx_slots"]), len(g["h_slots"]),
+                 len(g["ht_slots"]), len(g["cq_list"]), len(g["dq_list"]), sum(p is not None for p in g["pairs"]), sum(t is not None for t in g["triples"])))
+        print("wrote", out)
+        return
+    g = build()
+    out = a.out or os.path.join(PKG, "csrc", "hc_problem_gen.h")
     emit(g, out)
     t = build_tp(g)
     emit_tp(g, t, os.path.join(PKG, "csrc", "hc_problem_gen_tp.h"))

@@ -24,7 +24,7 @@ _lib = None
 # every symbol include/hcb200.h declares
 ABI_SYMBOLS = ("hcb200_workspace_bytes", "hcb200_abi_version", "hcb200_track", "hcb200_track_abort",
                "hcb200_build_target_params", "hcb200_score_tracks", "hcb200_refine_tracks", "hcb200_kernel_info", "hcb200_ffma_probe",
-               "hcb200_error_string", "hcb200_make_pose_record", "hcb200_reduce_pose_records", "hcb200_count_solutions")
+               "hcb200_error_string", "hcb200_make_pose_record", "hcb200_reduce_pose_records", "hcb200_count_solutions", "hcb200_problem_info")
 
 
 class HCB200Error(RuntimeError):
