@@ -38,6 +38,12 @@ extern "C" {
 
 /* flags */
 #define HCB200_FLAG_PRUNE_PATHS 1u   /* positive-depth path pruning (always on in the reference GPU kernels, …TrunPaths.cu:148-154) */
+/* Split long paths (ABI 3): a path that reaches 4/5 of the step cap while fresh paths are still queued is parked and finished by the first
+ * warp that runs out of fresh paths, so a round ends on many short remainders instead of a few long paths (default round: -5 % time).
+ * Results are bit-identical with and without the flag.  The caller promises that d_workspace holds hcb200_workspace_bytes_for(n_hyp) bytes
+ * (256 + 20 bytes per path) instead of hcb200_workspace_bytes().  Ignored by hcb200_track_abort.  Bits 16..31 of `flags`, when non-zero,
+ * replace the step at which a path is parked (tuning; default 4/5 of hc_max_steps). */
+#define HCB200_FLAG_SPLIT_LONG_PATHS 2u
 
 /* Optional per-path counters (all int32): HC steps attempted, predictor stages, corrector stages,
  * rejected steps | end reason << 16 (0 converged, 1 infinity, 2 pruned, 3 step cap, 4 skipped after abort). */
@@ -67,6 +73,7 @@ typedef struct {
 
 /* Device workspace the launches need (work counter + reduction scratch); zeroing is done by the launch itself. */
 size_t hcb200_workspace_bytes(void);
+size_t hcb200_workspace_bytes_for(int n_hyp);      /* workspace size that HCB200_FLAG_SPLIT_LONG_PATHS needs for rounds of up to n_hyp hypotheses */
 int hcb200_abi_version(void);
 
 /* The minimal problem compiled into this library (the reference reads these from problems/<name>/gpuhc_settings.yaml:

@@ -16,14 +16,20 @@
 
 namespace {
 
-// one workspace per device (the launches zero it themselves)
-void* workspace()
+// one workspace per device (the launches zero it themselves), grown when a larger round arrives; sized for HCB200_FLAG_SPLIT_LONG_PATHS
+void* workspace(int n_hyp = 0)
 {
   static void* ws[64] = {nullptr};
+  static size_t bytes[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return nullptr;
-  if (!ws[dev] && cudaMalloc(&ws[dev], hcb200_workspace_bytes()) != cudaSuccess) ws[dev] = nullptr;
+  const size_t need = hcb200_workspace_bytes_for(n_hyp);
+  if (!ws[dev] || bytes[dev] < need) {
+    if (ws[dev]) { cudaDeviceSynchronize(); cudaFree(ws[dev]); }
+    bytes[dev] = need;
+    if (cudaMalloc(&ws[dev], need) != cudaSuccess) { ws[dev] = nullptr; bytes[dev] = 0; }
+  }
   return ws[dev];
 }
 
@@ -57,10 +63,10 @@ real_Double_t track(magma_queue_t q, int n_hyp, int max_steps, int max_corr, int
 {
   cudaStream_t s = q->cuda_stream();
   report("hcb200_track",
-         hcb200_track(s, n_hyp, max_steps, max_corr, dt_inc, HCB200_FLAG_PRUNE_PATHS,
+         hcb200_track(s, n_hyp, max_steps, max_corr, dt_inc, HCB200_FLAG_PRUNE_PATHS | HCB200_FLAG_SPLIT_LONG_PATHS,
                       (const float*)first_entry(d_startSols_array, s), (const float*)d_startParams, (const float*)d_targetParams,
                       (const float*)d_diffParams, (float*)first_entry(d_Track_array, s), (uint8_t*)d_conv, (uint8_t*)d_inf,
-                      nullptr, workspace()));
+                      nullptr, workspace(n_hyp)));
   return 0.0;
 }
 

@@ -219,3 +219,28 @@ def test_non_default_hc_settings_bit_exact(tracker, oracle, ransac0, max_steps, 
             assert _bit_equal(tr_g[:, :30], tr_o[:, :30])
     finally:
         tracker.max_steps, tracker.max_corr, tracker.dt_inc = saved
+
+
+@pytest.mark.parametrize("prune", [True, False])
+def test_split_long_paths_gives_identical_results(problem, ransac0, prune):
+    """HCB200_FLAG_SPLIT_LONG_PATHS parks a path at a step boundary and resumes it on another warp: flags, end points and every counter must
+    be those of the unsplit kernel bit for bit, wherever the cut is made (step 1: every path is cut; 79: only step-capped ones; default 64)."""
+    H = 60
+    picked = hc.sample_hypotheses(3, H, ransac0["locations"].shape[0])
+    target, diff = hc.target_params_from_picks(picked, ransac0["locations"], ransac0["tangents"], problem["start_params"])
+    base = hc.Tracker(problem=problem, stats=True, split=False)
+    base.upload_params(target, diff)
+    base.track(H, prune=prune)
+    tr0, cv0, inf0, st0 = base.results(H)
+    assert (st0[:, 0] > 64).sum() > 1000                      # there ARE long paths to cut
+    trk = hc.Tracker(problem=problem, stats=True, split=True)
+    trk.upload_params(target, diff)
+    for cut in (0, 1, 2, 17, 64, 79, 80, 81):
+        trk.suspend_step = cut
+        trk.d_tracks.zero_(); trk.d_conv.fill_(7); trk.d_inf.fill_(7)
+        for rep in range(2):                                  # (twice: the launch must leave the workspace reusable)
+            trk.track(H, prune=prune)
+        tr, cv, inf, st = trk.results(H)
+        assert np.array_equal(cv, cv0) and np.array_equal(inf, inf0), cut
+        assert np.array_equal(st, st0), cut
+        assert _bit_equal(tr, tr0), cut

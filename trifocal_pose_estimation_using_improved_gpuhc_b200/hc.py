@@ -18,13 +18,15 @@ NUM_VARS = 30
 NUM_PARAMS = 33
 NUM_TRACKS = 312
 FLAG_PRUNE_PATHS = 1
+FLAG_SPLIT_LONG_PATHS = 2      # needs a workspace of hcb200_workspace_bytes_for(n_hyp) bytes
 
 _lib = None
 
 # every symbol include/hcb200.h declares
 ABI_SYMBOLS = ("hcb200_workspace_bytes", "hcb200_abi_version", "hcb200_track", "hcb200_track_abort",
                "hcb200_build_target_params", "hcb200_score_tracks", "hcb200_refine_tracks", "hcb200_kernel_info", "hcb200_ffma_probe",
-               "hcb200_error_string", "hcb200_make_pose_record", "hcb200_reduce_pose_records", "hcb200_count_solutions", "hcb200_problem_info")
+               "hcb200_error_string", "hcb200_make_pose_record", "hcb200_reduce_pose_records", "hcb200_count_solutions", "hcb200_problem_info",
+               "hcb200_workspace_bytes_for")
 
 
 class HCB200Error(RuntimeError):
@@ -43,6 +45,8 @@ def load_library(path=None):
     vp, i32, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint
     lib.hcb200_workspace_bytes.restype = ctypes.c_size_t
     lib.hcb200_workspace_bytes.argtypes = []
+    lib.hcb200_workspace_bytes_for.restype = ctypes.c_size_t
+    lib.hcb200_workspace_bytes_for.argtypes = [i32]
     lib.hcb200_abi_version.restype = i32
     lib.hcb200_error_string.restype = ctypes.c_char_p
     lib.hcb200_error_string.argtypes = [i32]
@@ -149,7 +153,7 @@ class Tracker:
     """Device-side state of one GPU's share of a RANSAC round (mirrors the per-GPU arrays of GPU_HC_Solver,
     GPU_HC_Solver.cpp:137-184) and the two launches.  All tensors are torch CUDA tensors owned by this object."""
 
-    def __init__(self, device=None, problem=None, max_steps=80, max_corr=3, dt_inc=4, stats=False):
+    def __init__(self, device=None, problem=None, max_steps=80, max_corr=3, dt_inc=4, stats=False, split=True):
         import torch
         self.torch = torch
         self.lib = load_library()
@@ -168,6 +172,7 @@ class Tracker:
         self.launches = 0
         self.want_stats = stats
         self.d_stats = None
+        self.split = bool(split)       # HCB200_FLAG_SPLIT_LONG_PATHS: long paths are parked and finished by idle warps (same results, shorter tail)
 
     def kernel_info(self, abort=False):
         v = [ctypes.c_int() for _ in range(5)]
@@ -191,6 +196,8 @@ class Tracker:
         self.d_found = torch.zeros(1, dtype=torch.uint8, device=dev)
         self.d_found_index = torch.empty(n_paths, dtype=torch.int32, device=dev)
         self.d_best = torch.zeros(16, dtype=torch.int32, device=dev)
+        if self.split:
+            self.d_ws = torch.zeros(int(self.lib.hcb200_workspace_bytes_for(n_hyp)), dtype=torch.uint8, device=dev)
         self.capacity = n_hyp
 
     def set_edgels(self, locations, K):
@@ -219,7 +226,7 @@ class Tracker:
         p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
         with self.torch.cuda.device(self.device):
             rc = self.lib.hcb200_track(self._stream(), n_hyp, self.max_steps, self.max_corr, self.dt_inc,
-                                       FLAG_PRUNE_PATHS if prune else 0,
+                                       (FLAG_PRUNE_PATHS if prune else 0) | (FLAG_SPLIT_LONG_PATHS if self.split else 0) | (int(getattr(self, "suspend_step", 0)) << 16),
                                        p(self.d_start_sols), p(self.d_start_params), p(self.d_target), p(self.d_diff),
                                        p(self.d_tracks), p(self.d_conv), p(self.d_inf), p(self.d_stats), p(self.d_ws))
         _check(rc, "hcb200_track")

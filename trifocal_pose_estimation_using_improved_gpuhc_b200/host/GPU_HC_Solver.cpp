@@ -61,6 +61,7 @@ GPU_HC_Solver::GPU_HC_Solver(YAML::Node cfg) : Problem_Setting_YAML_File(cfg)
   device_scoring                  = cfg.as_or<bool>("Device_Scoring", true);
   refine_iterations               = cfg.as_or<int>("Refine_Iterations", 0);
   device_statistics               = cfg.as_or<bool>("Device_Statistics", true);
+  split_long_paths                = cfg.as_or<bool>("Split_Long_Paths", true);
   // Lazy_Results: auto (default) | true | false.  When statistics and scoring run on the GPU the host needs 12 bytes per hypothesis and one
   // 128-byte record per GPU; the 248 bytes per path of end points are then copied back only when somebody asks for them (Track_Sols(),
   // Sol_Converge(), Sol_Infinity(), hcb200_solver_copy_results).  auto = lazy from 2048 hypotheses up.
@@ -146,7 +147,7 @@ void GPU_HC_Solver::Allocate_Arrays()
     HC_CUDA(cudaMalloc((void**)&d.d_tracks, sizeof(complex32) * V1 * (paths ? paths : 1)));
     HC_CUDA(cudaMalloc((void**)&d.d_conv, paths ? paths : 1));
     HC_CUDA(cudaMalloc((void**)&d.d_inf, paths ? paths : 1));
-    HC_CUDA(cudaMalloc(&d.d_ws, hcb200_workspace_bytes()));
+    HC_CUDA(cudaMalloc(&d.d_ws, split_long_paths ? hcb200_workspace_bytes_for(H) : hcb200_workspace_bytes()));
     // load the tracker kernels on this device now (CUDA loads modules lazily): the reference's timed region — launch to
     // sync, GPU_HC_Solver.cpp:384-446 — would otherwise include a one-off module load as long as the round itself
     { int regs = 0; hcb200_kernel_info(0, &regs, nullptr, nullptr, nullptr, nullptr); hcb200_kernel_info(1, &regs, nullptr, nullptr, nullptr, nullptr); }
@@ -346,7 +347,7 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
 {
   DeviceGuard keep_callers_device;
   if (verbose) std::cout << "GPU computing ..." << std::endl << std::endl;
-  const unsigned flags = prune_paths ? HCB200_FLAG_PRUNE_PATHS : 0u;
+  const unsigned flags = (prune_paths ? HCB200_FLAG_PRUNE_PATHS : 0u) | (split_long_paths ? HCB200_FLAG_SPLIT_LONG_PATHS : 0u);
   const size_t V1 = Num_Of_Vars + 1;
 
   multi_GPUs_time = wall_seconds();

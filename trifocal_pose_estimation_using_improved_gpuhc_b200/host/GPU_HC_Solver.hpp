@@ -143,6 +143,9 @@ private:
   // back instead of the host walking every end point.  The stacked pinned result arrays are allocated lazily, AFTER the tracker
   // launches, so that pinning gigabytes of host memory overlaps the GPU work instead of preceding it.
   bool device_statistics = true;
+  // Long paths are parked at 4/5 of the step cap and finished by idle warps (HCB200_FLAG_SPLIT_LONG_PATHS; YAML key Split_Long_Paths,
+  // default true): same results, the default round ends 3.6 % sooner.  Costs 20 bytes of device workspace per path.
+  bool split_long_paths = true;
   bool result_stacks_allocated = false;
   bool lazy_results = false, results_on_host = false;
   hcb200::complex32 h_selected_track[32];

@@ -13,7 +13,7 @@ import subprocess
 
 import numpy as np
 
-from .hc import FLAG_PRUNE_PATHS, HCB200Error
+from .hc import FLAG_PRUNE_PATHS, FLAG_SPLIT_LONG_PATHS, HCB200Error
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
@@ -48,6 +48,8 @@ def load_problem_library(path):
     lib = ctypes.CDLL(path)
     vp, i32, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint
     lib.hcb200_workspace_bytes.restype = ctypes.c_size_t
+    lib.hcb200_workspace_bytes_for.restype = ctypes.c_size_t
+    lib.hcb200_workspace_bytes_for.argtypes = [i32]
     lib.hcb200_error_string.restype = ctypes.c_char_p
     lib.hcb200_error_string.argtypes = [i32]
     lib.hcb200_problem_info.restype = i32
@@ -74,7 +76,7 @@ class ProblemTracker:
     """Device state and launches for one compiled problem: every hypothesis is one set of target parameters, every hypothesis tracks all
     Num_Of_Tracks start solutions (the same batch layout as the trifocal path: tracks [H*T][N+1], flags [H*T])."""
 
-    def __init__(self, problem_dir, problem=None, device=None, max_steps=80, max_corr=3, dt_inc=4, stats=False):
+    def __init__(self, problem_dir, problem=None, device=None, max_steps=80, max_corr=3, dt_inc=4, stats=False, split=True):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
@@ -96,6 +98,7 @@ class ProblemTracker:
             self.d_start_params = torch.view_as_real(torch.from_numpy(self.start_params_h)).contiguous().to(self.device)
             self.d_ws = torch.zeros(int(self.lib.hcb200_workspace_bytes()), dtype=torch.uint8, device=self.device)
         self.want_stats = stats
+        self.split = bool(split)
         self.capacity = 0
 
     def _check(self, code, what):
@@ -126,6 +129,8 @@ class ProblemTracker:
             self.d_stats = torch.empty((P, 4), dtype=torch.int32, device=dev) if self.want_stats else None
             self.d_counts = torch.empty((H, 3), dtype=torch.int32, device=dev)
             self.d_sums = torch.empty((P, 2), dtype=torch.float32, device=dev)
+            if self.split:
+                self.d_ws = torch.zeros(int(self.lib.hcb200_workspace_bytes_for(H)), dtype=torch.uint8, device=dev)
             self.capacity = H
         self.d_target[:H].copy_(torch.view_as_real(torch.from_numpy(target)))
         self.d_diff[:H].copy_(torch.view_as_real(torch.from_numpy(self.diff_params(target))))
@@ -137,7 +142,8 @@ class ProblemTracker:
     def track(self, n_hyp, prune=False):
         p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
         with self.torch.cuda.device(self.device):
-            rc = self.lib.hcb200_track(self._stream(), n_hyp, self.max_steps, self.max_corr, self.dt_inc, FLAG_PRUNE_PATHS if prune else 0,
+            rc = self.lib.hcb200_track(self._stream(), n_hyp, self.max_steps, self.max_corr, self.dt_inc,
+                                       (FLAG_PRUNE_PATHS if prune else 0) | (FLAG_SPLIT_LONG_PATHS if self.split else 0),
                                        p(self.d_start_sols), p(self.d_start_params), p(self.d_target), p(self.d_diff),
                                        p(self.d_tracks), p(self.d_conv), p(self.d_inf), p(self.d_stats), p(self.d_ws))
         self._check(rc, "hcb200_track")
