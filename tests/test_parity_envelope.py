@@ -130,11 +130,15 @@ def test_differences_from_the_committed_reference_gpu_flags_are_unstable_paths(H
     diff = (_bits(e["spec_conv"], P) != _bits(r["converged_bits"], P)) | (_bits(e["spec_inf"], P) != _bits(r["infinity_bits"], P)) | \
            (_bits(e["spec_real"], P) != _bits(r["real_bits"], P))
     _check(diff, unstable, "reference GPU-HC++ kernels (committed flags), %d hypotheses" % H, max_outside=MAX_OUTSIDE[key],
-           min_coverage=0.95 if H == 100 else 0.80)
+           min_coverage=MIN_COVERAGE[key], min_stable_agreement=MIN_STABLE[key])
 
 
 # observed stragglers (paths that differ from a reference implementation but flip in none of the variants), with 1.5x head-room
-MAX_OUTSIDE = {"gpu_h100": 3, "gpu_h1000": 60, "cpu_noprune": 6, "cpu_prune": 2}     # observed: 2, (see profiles), 4, 1
+MAX_OUTSIDE = {"gpu_h100": 3, "gpu_h1000": 116, "cpu_noprune": 6, "cpu_prune": 2}     # observed: 2, 77 (16 variants only), 4, 1
+# 1000 hypotheses: the committed envelope holds 16 variants (5.5 CPU-minutes each), so its unstable set is less saturated (1.30 % of the paths
+# against 1.87 % with 75 variants at 100 hypotheses): 94.4 % of the differences fall inside it, stable paths agree to 0.99975.
+MIN_COVERAGE = {"gpu_h100": 0.95, "gpu_h1000": 0.90}
+MIN_STABLE = {"gpu_h100": 0.9998, "gpu_h1000": 0.9996}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -175,7 +179,7 @@ def test_differences_from_the_reference_gpu_kernels_are_unstable_paths(problem, 
     unstable = _bits(e["unstable"], P)
     diff = (cv != cv_r) | (inf != inf_r) | (_real(tr, cv) != _real(tr_r, cv_r))
     _check(diff, unstable, "reference GPU-HC++ kernels, %d hypotheses" % H, max_outside=MAX_OUTSIDE[key],
-           min_coverage=0.95 if H == 100 else 0.80, min_stable_agreement=0.9998)
+           min_coverage=MIN_COVERAGE[key], min_stable_agreement=MIN_STABLE[key])
     # per hypothesis: counts over the STABLE paths are identical in every hypothesis but the stragglers'
     s = ~unstable
     for flag_a, flag_b in ((cv, cv_r), (inf, inf_r), (_real(tr, cv), _real(tr_r, cv_r))):

@@ -38,7 +38,35 @@ STRUCTURED = [
 ]
 
 
+def merge(base_path, ext_path, ext_raw_path, out):
+    """Union of an envelope file and an extension run (--structured 0 --seed-start K --raw …) of the same round: variant 0 of the extension
+    is the spec again and is dropped; the growth curve continues exactly (from the extension's raw flags)."""
+    b, e, r = np.load(base_path), np.load(ext_path), np.load(ext_raw_path)
+    assert np.array_equal(b["picked"], e["picked"]) and bool(b["prune"][0]) == bool(e["prune"][0])
+    assert np.array_equal(b["spec_conv"], e["spec_conv"]) and np.array_equal(b["spec_inf"], e["spec_inf"]) and np.array_equal(b["spec_real"], e["spec_real"])
+    P = len(b["flips"])
+    unb = lambda a: np.unpackbits(a, axis=-1)[..., :P].astype(bool)
+    conv, inf, real = unb(r["conv"]), unb(r["inf"]), unb(r["real"])
+    acc = unb(b["unstable"]).copy()
+    growth = list(b["growth"])
+    for k in range(1, conv.shape[0]):
+        acc |= (conv[k] != conv[0]) | (inf[k] != inf[0]) | (real[k] != real[0])
+        growth.append(int(acc.sum()))
+    unstable = unb(b["unstable"]) | unb(e["unstable"])
+    assert np.array_equal(acc, unstable)
+    cat = lambda k: np.concatenate([b[k], e[k][1:]])
+    np.savez_compressed(out, names=cat("names"), picked=b["picked"], prune=b["prune"], spec_conv=b["spec_conv"], spec_inf=b["spec_inf"], spec_real=b["spec_real"],
+                        unstable=np.packbits(unstable), flips=(b["flips"].astype(np.uint32) + e["flips"]).astype(np.uint16),
+                        head_conv=cat("head_conv"), head_inf=cat("head_inf"), variant_fields=cat("variant_fields"),
+                        seq_unstable=np.packbits(unb(b["seq_unstable"]) | unb(e["seq_unstable"])), growth=np.array(growth, np.int32),
+                        variant_counts=cat("variant_counts"), variant_flips=cat("variant_flips"))
+    print("merged %d + %d variants -> %s: unstable %d -> %d of %d paths" % (len(b["names"]), len(e["names"]) - 1, out, unb(b["unstable"]).sum(), unstable.sum(), P))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--merge":         # --merge BASE EXT EXT_RAW OUT
+        merge(*sys.argv[2:6])
+        return
     ap = argparse.ArgumentParser()
     ap.add_argument("--hyp", type=int, default=100)
     ap.add_argument("--seeds", type=int, default=64, help="number of stochastic-arithmetic variants")

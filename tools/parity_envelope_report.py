@@ -153,12 +153,12 @@ def main():
     w("grows by ~1 path per extra stochastic seed, see the growth table) — each is listed with both sides' record of where the path stopped.")
     w("")
     summary = []
-    for prune in ("prune", "noprune"):
-        f = os.path.join(GOLD, "envelope_seed0_h100_%s.npz" % prune)
+    for H, prune in ((100, "prune"), (100, "noprune"), (1000, "prune")):
+        f = os.path.join(GOLD, "envelope_seed0_h%d_%s.npz" % (H, prune))
         if not os.path.exists(f):
             continue
         e = np.load(f)
-        w("## Envelope, 100 hypotheses, pruning %s: %d variants, %d unstable paths (%.2f %%)" % ("on" if prune == "prune" else "off", len(e["names"]), bits(e["unstable"], 31200).sum(), 100.0 * bits(e["unstable"], 31200).mean()))
+        w("## Envelope, %d hypotheses, pruning %s: %d variants, %d unstable paths (%.2f %%)" % (H, "on" if prune == "prune" else "off", len(e["names"]), bits(e["unstable"], H * TR).sum(), 100.0 * bits(e["unstable"], H * TR).mean()))
         w("")
         w("| variant | converged | infinity | real | conv flips vs spec | inf flips | real flips | unstable set after this variant |")
         w("|---|---:|---:|---:|---:|---:|---:|---:|")
@@ -170,13 +170,14 @@ def main():
             w("| %s | %d | %d | %d | %d | %d | %d | %d |" % ((n,) + tuple(e["variant_counts"][k]) + tuple(e["variant_flips"][k]) + (e["growth"][k],)))
         vf = e["variant_flips"][seeds]
         vc = e["variant_counts"][seeds]
-        w("| ulp perturbation seeds %d..%d (min–max) | %d–%d | %d–%d | %d–%d | %d–%d | %d–%d | %d–%d | %d |" % (
-            4, len(seeds), vc[:, 0].min(), vc[:, 0].max(), vc[:, 1].min(), vc[:, 1].max(), vc[:, 2].min(), vc[:, 2].max(),
-            vf[:, 0].min(), vf[:, 0].max(), vf[:, 1].min(), vf[:, 1].max(), vf[:, 2].min(), vf[:, 2].max(), e["growth"][-1]))
+        if len(seeds) > 3:
+            w("| ulp perturbation seeds %d..%d (min–max) | %d–%d | %d–%d | %d–%d | %d–%d | %d–%d | %d–%d | %d |" % (
+                4, len(seeds), vc[:, 0].min(), vc[:, 0].max(), vc[:, 1].min(), vc[:, 1].max(), vc[:, 2].min(), vc[:, 2].max(),
+                vf[:, 0].min(), vf[:, 0].max(), vf[:, 1].min(), vf[:, 1].max(), vf[:, 2].min(), vf[:, 2].max(), e["growth"][-1]))
         w("")
         g = e["growth"]
-        tail = [int(g[k] - g[k - 1]) for k in range(len(g) - 10, len(g))]
-        w("Growth of the unstable set over the last ten variants: +%s paths — the tail of rarely-flipping paths is not exhausted, which is" % ", +".join(str(t) for t in tail))
+        tail = [int(g[k] - g[k - 1]) for k in range(max(1, len(g) - 10), len(g))]
+        w("Growth of the unstable set over the last variants: +%s paths — the tail of rarely-flipping paths is not exhausted, which is" % ", +".join(str(t) for t in tail))
         w("where the stragglers come from.  Flip-count histogram of the unstable paths (in how many of the %d variants a path differs from the spec):" % (len(names) - 1))
         fl = e["flips"][e["flips"] > 0]
         hist = [(1, 1), (2, 3), (4, 9), (10, 29), (30, 10 ** 6)]
