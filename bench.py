@@ -42,7 +42,7 @@ NOMINAL_FP32_TFLOPS = 74.4     # 148 SMs x 128 lanes x 2 flop x 1.965 GHz
 # beside the dense-LU model above, which also counts the structural zeros the kernel skips.
 EXEC_FLOP_PER_STAGE = 54772.0
 EXEC_SOURCE = "profiles/ncu_r2.md: executed FP32 thread instructions of the final kernel per HC stage (FMA = 2 flop), x stages / kernel time"
-TRAFFIC_BYTES_H100 = 199168
+TRAFFIC_BYTES_H100 = 821760
 TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one tracker launch of the default round, ncu --set full capture of the final "
                   "kernel (profiles/ncu_r2.md); the 7.8 MB of results stay in the 126 MB L2, so traffic < algorithmic bytes")
 
