@@ -40,9 +40,9 @@ $(LIBDIR)/libhcb200_host.so: $(HOST_SRCS) $(HOST_HDRS) $(LIBDIR)/libhcb200.so
 	g++ -std=c++17 -O2 -fPIC -shared -Wall -o $@ $(HOST_SRCS) -Iinclude -I$(CUDA)/include \
 	  -L$(LIBDIR) -lhcb200 -L$(CUDA)/lib64 -lcudart -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,$(CUDA)/lib64
 
-$(LIBDIR)/hc-main: $(HOST)/main.cpp $(LIBDIR)/libhcb200_host.so
-	g++ -std=c++17 -O2 -Wall -o $@ $(HOST)/main.cpp -Iinclude -I$(CUDA)/include -L$(LIBDIR) -lhcb200_host -lhcb200 \
-	  -L$(CUDA)/lib64 -lcudart -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,$(CUDA)/lib64
+$(LIBDIR)/hc-main: $(HOST)/main.cpp $(HOST)/generic_problem.cpp $(LIBDIR)/libhcb200_host.so
+	g++ -std=c++17 -O2 -Wall -o $@ $(HOST)/main.cpp $(HOST)/generic_problem.cpp -Iinclude -I$(CUDA)/include -L$(LIBDIR) -lhcb200_host -lhcb200 \
+	  -L$(CUDA)/lib64 -lcudart -ldl -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,$(CUDA)/lib64
 
 oracle:
 	$(MAKE) -C oracle oracle

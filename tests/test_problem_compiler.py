@@ -202,3 +202,42 @@ def test_gpu_tracker_of_a_compiled_problem_is_bit_identical_to_the_oracle(name):
     rc = trk.lib.hcb200_track_abort(None, 1, 10, 80, 3, 4, 0, *([None] * 14))
     assert rc != 0 and b"not supported" in trk.lib.hcb200_error_string(rc).lower()
     torch.cuda.synchronize()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", PROBLEMS)
+def test_hc_main_runs_a_compiled_problem(name, tmp_path):
+    """`hc-main -p <name>` — the original GPU-HC usage (reference README.md:25): the folder's start system is tracked to target_params.txt with
+    the library compiled from the folder; statistics file and converged end points equal the oracle's (bit for bit: %.9g round-trips float32)."""
+    import shutil
+    from oracle.pyoracle import Oracle
+    exe = os.path.join(PKG, "lib", "hc-main")
+    root = str(tmp_path)
+    shutil.copytree(_pdir(name), os.path.join(root, "problems", name))
+    os.makedirs(os.path.join(root, "Output_Write_Files"))
+    prob, tgt, dif = _inputs(name, 1)
+    n, T = prob["spec"]["n_vars"], prob["spec"]["n_tracks"]
+    tr_o, cv_o, inf_o, st_o = Oracle(prob, problem_dir=_pdir(name)).track(tgt, dif, False)
+    real_o = (cv_o != 0) & np.all(np.abs(tr_o[:, :n].imag).astype(np.float64) <= 1e-4, axis=1)
+    for H in (1, 37):
+        out = subprocess.run([exe, "-p", name, "-d", root, "-s", "Num_Of_RANSAC_Iterations=%d" % H], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        stats = [int(v) for v in open(os.path.join(root, "Output_Write_Files", "GPU_Sols_Statistics.txt")).read().split()]
+        assert stats == [H * int(cv_o.sum()), H * int(real_o.sum()), H * int(inf_o.sum())]          # converged <TAB> real <TAB> infinity
+        assert float(open(os.path.join(root, "Output_Write_Files", "GPU_Timings.txt")).read()) > 0.0
+    got, cur = {}, None
+    for line in open(os.path.join(root, "Output_Write_Files", "GPU_Converged_HC_Tracks.txt")):
+        if line.startswith("track"):
+            cur = int(line.split()[1]); got[cur] = []
+        else:
+            re_, im_ = line.split(); got[cur].append(np.float32(re_) + 1j * np.float32(im_))
+    assert sorted(got) == np.nonzero(cv_o)[0].tolist()
+    for t, x in got.items():
+        assert np.array_equal(np.asarray(x, np.complex64).view(np.uint64), np.ascontiguousarray(tr_o[t, :n]).view(np.uint64)), t
+    # a folder nobody compiled is refused with a message, not tracked by something else
+    shutil.copytree(_pdir(name), os.path.join(root, "problems", "uncompiled"))
+    y = os.path.join(root, "problems", "uncompiled", "gpuhc_settings.yaml")
+    text = open(y).read().replace("problem_name: " + name, "problem_name: uncompiled")
+    open(y, "w").write(text)
+    out = subprocess.run([exe, "-p", "uncompiled", "-d", root], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "make problem" in out.stdout + out.stderr

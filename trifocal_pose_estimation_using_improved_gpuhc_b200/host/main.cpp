@@ -13,11 +13,14 @@
 
 #include "GPU_HC_Solver.hpp"
 
+bool run_compiled_problem(YAML::Node settings, const std::string& root);      // generic_problem.cpp: -p <a problem other than the trifocal one>
+
 static void print_help()
 {
   std::printf("Usage: ./hc-main [options]\n\noptions:\n"
               "  -h, --help            show this help message and exit\n"
-              "  -p, --problem NAME    problem folder name under <root>/problems (trifocal_2op1p_30x30)\n"
+              "  -p, --problem NAME    problem folder name under <root>/problems (trifocal_2op1p_30x30: the RANSAC pipeline; any other\n"
+              "                        folder: tracked to its target_params.txt with the library compiled by `make problem PROBLEM_DIR=...`)\n"
               "  -d, --directory ROOT  repository root holding problems/, RANSAC_Data/, Output_Write_Files/ (default ../../)\n"
               "  -s, --set KEY=VALUE   override one settings key (repeatable)\n");
 }
@@ -99,5 +102,11 @@ int main(int argc, char** argv)
     std::cerr << "Exception: " << e.what() << std::endl;
     return 0;
   }
-  return run_GPU_HC_Solver(settings, root) ? 0 : 1;
+  try {
+    if (settings["problem_name"].as<std::string>() != "trifocal_2op1p_30x30") return run_compiled_problem(settings, root) ? 0 : 1;
+    return run_GPU_HC_Solver(settings, root) ? 0 : 1;
+  } catch (const std::exception& e) {          // a missing / malformed settings key
+    std::cerr << "Exception: " << e.what() << std::endl;
+    return 1;
+  }
 }
