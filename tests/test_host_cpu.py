@@ -28,7 +28,11 @@ def test_device_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "libhcb200.so does not export " + n
     assert set(names) == set(hc.ABI_SYMBOLS)
     assert lib.hcb200_abi_version() == 3
-    assert lib.hcb200_workspace_bytes() >= 16
+    assert lib.hcb200_workspace_bytes() == 256
+    # split-long-paths workspace: 256 + a list entry (4 bytes, padded to 16) + 16 bytes of parked state per path; host-only functions
+    assert lib.hcb200_workspace_bytes_for(0) == 256 and lib.hcb200_workspace_bytes_for(-3) == 256
+    assert lib.hcb200_workspace_bytes_for(100) == 256 + 31200 * 4 + 31200 * 16
+    assert lib.hcb200_workspace_bytes_for(1) == 256 + 1248 + 312 * 16 and lib.hcb200_workspace_bytes_for(3) % 16 == 0
 
 
 def test_host_library_exports_every_declared_symbol():
