@@ -42,7 +42,10 @@ extern "C" {
  * warp that runs out of fresh paths, so a round ends on many short remainders instead of a few long paths (default round: -5 % time).
  * Results are bit-identical with and without the flag.  The caller promises that d_workspace holds hcb200_workspace_bytes_for(n_hyp) bytes
  * (256 + 20 bytes per path) instead of hcb200_workspace_bytes().  Ignored by hcb200_track_abort.  Bits 16..31 of `flags`, when non-zero,
- * replace the step at which a path is parked (tuning; default 4/5 of hc_max_steps). */
+ * replace the step at which a path is parked (tuning; default 4/5 of hc_max_steps).  The launcher uses the split kernel only while the round
+ * is small (fewer than 48 paths per resident warp: about 450 hypotheses on a B200), so callers need not pay for the large workspace of big
+ * rounds: pass the flag only when n_hyp <= HCB200_SPLIT_MAX_HYPOTHESES. */
+#define HCB200_SPLIT_MAX_HYPOTHESES 2048
 #define HCB200_FLAG_SPLIT_LONG_PATHS 2u
 
 /* Optional per-path counters (all int32): HC steps attempted, predictor stages, corrector stages,

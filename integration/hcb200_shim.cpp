@@ -24,7 +24,7 @@ void* workspace(int n_hyp = 0)
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return nullptr;
-  const size_t need = hcb200_workspace_bytes_for(n_hyp);
+  const size_t need = n_hyp <= HCB200_SPLIT_MAX_HYPOTHESES ? hcb200_workspace_bytes_for(n_hyp) : hcb200_workspace_bytes();
   if (!ws[dev] || bytes[dev] < need) {
     if (ws[dev]) { cudaDeviceSynchronize(); cudaFree(ws[dev]); }
     bytes[dev] = need;
@@ -63,7 +63,8 @@ real_Double_t track(magma_queue_t q, int n_hyp, int max_steps, int max_corr, int
 {
   cudaStream_t s = q->cuda_stream();
   report("hcb200_track",
-         hcb200_track(s, n_hyp, max_steps, max_corr, dt_inc, HCB200_FLAG_PRUNE_PATHS | HCB200_FLAG_SPLIT_LONG_PATHS,
+         hcb200_track(s, n_hyp, max_steps, max_corr, dt_inc,
+                      HCB200_FLAG_PRUNE_PATHS | (n_hyp <= HCB200_SPLIT_MAX_HYPOTHESES ? HCB200_FLAG_SPLIT_LONG_PATHS : 0u),
                       (const float*)first_entry(d_startSols_array, s), (const float*)d_startParams, (const float*)d_targetParams,
                       (const float*)d_diffParams, (float*)first_entry(d_Track_array, s), (uint8_t*)d_conv, (uint8_t*)d_inf,
                       nullptr, workspace(n_hyp)));

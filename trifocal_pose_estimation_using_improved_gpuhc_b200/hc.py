@@ -19,6 +19,7 @@ NUM_PARAMS = 33
 NUM_TRACKS = 312
 FLAG_PRUNE_PATHS = 1
 FLAG_SPLIT_LONG_PATHS = 2      # needs a workspace of hcb200_workspace_bytes_for(n_hyp) bytes
+SPLIT_MAX_HYPOTHESES = 2048    # HCB200_SPLIT_MAX_HYPOTHESES: larger rounds never use the split kernel, so they are not given its workspace
 
 _lib = None
 
@@ -197,7 +198,7 @@ class Tracker:
         self.d_found_index = torch.empty(n_paths, dtype=torch.int32, device=dev)
         self.d_best = torch.zeros(16, dtype=torch.int32, device=dev)
         if self.split:
-            self.d_ws = torch.zeros(int(self.lib.hcb200_workspace_bytes_for(n_hyp)), dtype=torch.uint8, device=dev)
+            self.d_ws = torch.zeros(int(self.lib.hcb200_workspace_bytes_for(min(n_hyp, SPLIT_MAX_HYPOTHESES))), dtype=torch.uint8, device=dev)
         self.capacity = n_hyp
 
     def set_edgels(self, locations, K):
@@ -226,7 +227,8 @@ class Tracker:
         p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
         with self.torch.cuda.device(self.device):
             rc = self.lib.hcb200_track(self._stream(), n_hyp, self.max_steps, self.max_corr, self.dt_inc,
-                                       (FLAG_PRUNE_PATHS if prune else 0) | (FLAG_SPLIT_LONG_PATHS if self.split else 0) | (int(getattr(self, "suspend_step", 0)) << 16),
+                                       (FLAG_PRUNE_PATHS if prune else 0) | (FLAG_SPLIT_LONG_PATHS if (self.split and n_hyp <= SPLIT_MAX_HYPOTHESES) else 0) |
+                                       (int(getattr(self, "suspend_step", 0)) << 16),
                                        p(self.d_start_sols), p(self.d_start_params), p(self.d_target), p(self.d_diff),
                                        p(self.d_tracks), p(self.d_conv), p(self.d_inf), p(self.d_stats), p(self.d_ws))
         _check(rc, "hcb200_track")

@@ -147,7 +147,7 @@ void GPU_HC_Solver::Allocate_Arrays()
     HC_CUDA(cudaMalloc((void**)&d.d_tracks, sizeof(complex32) * V1 * (paths ? paths : 1)));
     HC_CUDA(cudaMalloc((void**)&d.d_conv, paths ? paths : 1));
     HC_CUDA(cudaMalloc((void**)&d.d_inf, paths ? paths : 1));
-    HC_CUDA(cudaMalloc(&d.d_ws, split_long_paths ? hcb200_workspace_bytes_for(H) : hcb200_workspace_bytes()));
+    HC_CUDA(cudaMalloc(&d.d_ws, (split_long_paths && H <= HCB200_SPLIT_MAX_HYPOTHESES) ? hcb200_workspace_bytes_for(H) : hcb200_workspace_bytes()));
     // load the tracker kernels on this device now (CUDA loads modules lazily): the reference's timed region — launch to
     // sync, GPU_HC_Solver.cpp:384-446 — would otherwise include a one-off module load as long as the round itself
     { int regs = 0; hcb200_kernel_info(0, &regs, nullptr, nullptr, nullptr, nullptr); hcb200_kernel_info(1, &regs, nullptr, nullptr, nullptr, nullptr); }
@@ -347,7 +347,7 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
 {
   DeviceGuard keep_callers_device;
   if (verbose) std::cout << "GPU computing ..." << std::endl << std::endl;
-  const unsigned flags = (prune_paths ? HCB200_FLAG_PRUNE_PATHS : 0u) | (split_long_paths ? HCB200_FLAG_SPLIT_LONG_PATHS : 0u);
+  const unsigned prune_flag = prune_paths ? HCB200_FLAG_PRUNE_PATHS : 0u;
   const size_t V1 = Num_Of_Vars + 1;
 
   multi_GPUs_time = wall_seconds();
@@ -357,6 +357,7 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
     HC_CUDA(cudaSetDevice(d.device));
     HC_CUDA(cudaEventRecord((cudaEvent_t)d.ev_start, (cudaStream_t)d.stream));
     int rc;
+    const unsigned flags = prune_flag | ((split_long_paths && sub_RANSAC_iters[g] <= HCB200_SPLIT_MAX_HYPOTHESES) ? HCB200_FLAG_SPLIT_LONG_PATHS : 0u);
     if (Abort_RANSAC_by_Good_Sol)
       rc = hcb200_track_abort(d.stream, sub_RANSAC_iters[g], Num_Of_Triplet_Edgels, GPUHC_Max_Steps, GPUHC_Max_Correction_Steps,
                               GPUHC_delta_t_incremental_steps, flags, d.d_start_sols, d.d_start_params, d.d_target, d.d_diff,

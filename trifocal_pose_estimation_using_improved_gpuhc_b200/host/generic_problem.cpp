@@ -74,7 +74,7 @@ bool run_compiled_problem(YAML::Node cfg, const std::string& root)
   const int dt_inc = cfg["GPUHC_Num_Of_Steps_to_Increase_Delta_t"].as<int>();
   const int H = cfg.as_or<int>("Num_Of_RANSAC_Iterations", 1);
   const bool prune = cfg.as_or<bool>("Prune_Paths", false);
-  const bool split = cfg.as_or<bool>("Split_Long_Paths", true);
+  const bool split = cfg.as_or<bool>("Split_Long_Paths", true) && H <= HCB200_SPLIT_MAX_HYPOTHESES;
   if (H < 1) { hcb200::log_error("Num_Of_RANSAC_Iterations must be >= 1"); return false; }
 
   ProblemLibrary L;
@@ -118,7 +118,7 @@ bool run_compiled_problem(YAML::Node cfg, const std::string& root)
   GP_CUDA(cudaMalloc((void**)&d_cv, paths));
   GP_CUDA(cudaMalloc((void**)&d_inf, paths));
   GP_CUDA(cudaMalloc((void**)&d_counts, sizeof(unsigned) * 3 * H));
-  GP_CUDA(cudaMalloc(&d_ws, L.workspace_bytes_for(H)));
+  GP_CUDA(cudaMalloc(&d_ws, L.workspace_bytes_for(split ? H : 0)));
   GP_CUDA(cudaMemcpyAsync(d_ss, start_sols.data(), sizeof(complex32) * T * V1, cudaMemcpyHostToDevice, s));
   GP_CUDA(cudaMemcpyAsync(d_sp, start_params.data(), sizeof(complex32) * P1, cudaMemcpyHostToDevice, s));
   GP_CUDA(cudaMemcpyAsync(d_tp, targets.data(), sizeof(complex32) * H * P1, cudaMemcpyHostToDevice, s));

@@ -13,7 +13,7 @@ import subprocess
 
 import numpy as np
 
-from .hc import FLAG_PRUNE_PATHS, FLAG_SPLIT_LONG_PATHS, HCB200Error
+from .hc import FLAG_PRUNE_PATHS, FLAG_SPLIT_LONG_PATHS, SPLIT_MAX_HYPOTHESES, HCB200Error
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
@@ -130,7 +130,7 @@ class ProblemTracker:
             self.d_counts = torch.empty((H, 3), dtype=torch.int32, device=dev)
             self.d_sums = torch.empty((P, 2), dtype=torch.float32, device=dev)
             if self.split:
-                self.d_ws = torch.zeros(int(self.lib.hcb200_workspace_bytes_for(H)), dtype=torch.uint8, device=dev)
+                self.d_ws = torch.zeros(int(self.lib.hcb200_workspace_bytes_for(min(H, SPLIT_MAX_HYPOTHESES))), dtype=torch.uint8, device=dev)
             self.capacity = H
         self.d_target[:H].copy_(torch.view_as_real(torch.from_numpy(target)))
         self.d_diff[:H].copy_(torch.view_as_real(torch.from_numpy(self.diff_params(target))))
@@ -143,7 +143,7 @@ class ProblemTracker:
         p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
         with self.torch.cuda.device(self.device):
             rc = self.lib.hcb200_track(self._stream(), n_hyp, self.max_steps, self.max_corr, self.dt_inc,
-                                       (FLAG_PRUNE_PATHS if prune else 0) | (FLAG_SPLIT_LONG_PATHS if self.split else 0),
+                                       (FLAG_PRUNE_PATHS if prune else 0) | (FLAG_SPLIT_LONG_PATHS if (self.split and n_hyp <= SPLIT_MAX_HYPOTHESES) else 0),
                                        p(self.d_start_sols), p(self.d_start_params), p(self.d_target), p(self.d_diff),
                                        p(self.d_tracks), p(self.d_conv), p(self.d_inf), p(self.d_stats), p(self.d_ws))
         self._check(rc, "hcb200_track")
