@@ -232,6 +232,18 @@ def host_class_leg(n_gpus, abort):
         r = s.round(fetch=False)
         s.close()
         out["h10000"] = {"multi_GPUs_time_ms": r["seconds"] * 1e3, "value": 10000 / r["seconds"], "unit": "hypotheses/s"}
+        if n_gpus > 1:
+            # early abort on a 10 000-hypothesis round: the reference's per-GPU flag against the flag shared over NVLink peer mappings
+            ab = {}
+            for key, ov in (("per_gpu_flag", ""), ("shared_flag", ";Abort_Across_GPUs=true")):
+                s = HostSolver(tmp, "Num_Of_GPUs=%d;Num_Of_RANSAC_Iterations=10000;Abort_RANSAC_by_Good_Sol=true%s" % (n_gpus, ov))
+                s.round(fetch=False)
+                secs = [s.round(fetch=False)["seconds"] for _ in range(3)]
+                r = s.round(fetch=False)
+                s.close()
+                ab[key] = {"ms": float(np.mean(secs)) * 1e3, "pose_found": int(r["pose_found"]), "first_passing_path": int(r["best"][1]),
+                           "paths_converged_before_stop": int(r["totals"][0])}
+            out["abort_h10000"] = ab
     return out
 
 

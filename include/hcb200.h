@@ -115,6 +115,26 @@ int hcb200_track_abort(void* stream, int n_hyp, int n_edgels,
                        uint8_t* d_found, int32_t* d_found_index, hcb200_best_record* d_best,
                        hcb200_path_stats* d_stats, void* d_workspace);
 
+/* Early abort ACROSS the GPUs of one process (ABI 3).  The reference keeps the flag per GPU (GPU_HC_Solver.cpp:329,402): a GPU whose shard holds
+ * no good hypothesis tracks all of it while another GPU has long found the pose.  Here the first passing path also raises the flags of the
+ * peer GPUs: d_peer_found[i] (host array of n_peers <= 7 device pointers) are the d_found bytes of the other GPUs' launches of the same round,
+ * written through NVLink peer mappings — the caller enables peer access (cudaDeviceEnablePeerAccess) and resets every flag before the first
+ * launch of the round.  Each GPU still polls only its own flag.  A GPU stopped by a peer reports found == 0 in its own best record and leaves
+ * d_found_index at -1; its d_found byte reads 1. */
+int hcb200_track_abort_peers(void* stream, int n_hyp, int n_edgels,
+                       int hc_max_steps, int hc_max_correction_steps, int hc_delta_t_incremental_steps, unsigned flags,
+                       const float* d_start_sols, const float* d_start_params,
+                       const float* d_target_params, const float* d_diff_params,
+                       const float* d_edgel_locations, const float* d_intrinsic,
+                       float* d_tracks, uint8_t* d_converged, uint8_t* d_infinity,
+                       uint8_t* d_found, int32_t* d_found_index, hcb200_best_record* d_best,
+                       hcb200_path_stats* d_stats, void* d_workspace,
+                             uint8_t* const* d_peer_found, int n_peers);
+
+/* Lets kernels running on `device` store into memory of `peer_device` (cudaDeviceEnablePeerAccess in `device`'s context; "already enabled" is
+ * success; cudaErrorPeerAccessUnsupported when the two GPUs have no peer path).  Needed once per ordered pair before hcb200_track_abort_peers. */
+int hcb200_enable_peer_access(int device, int peer_device);
+
 /* Device-side hypothesis generation (Prepare_Target_Params at scale, GPU_HC_Solver.cpp:252-306): given the picked
  * edgel indices [n_hyp][3] it gathers the 34 target parameters and target - start for every hypothesis. */
 int hcb200_build_target_params(void* stream, int n_hyp, const int32_t* d_picked, int n_edgels,

@@ -236,6 +236,30 @@ def test_host_class_two_gpus_same_answer(tree):
     assert np.array_equal(r["per"].astype(np.int32), g["counts"])
 
 
+def test_host_class_abort_across_gpus(tree):
+    """Abort_Across_GPUs (hcb200_track_abort_peers): with the reference's per-GPU flag a 4 000-hypothesis abort round on two GPUs lasts until BOTH
+    shards have met a good hypothesis of their own; with the flag shared over NVLink it lasts until the FIRST one has.  Same pose either way."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = {}
+    for key, ov in (("per_gpu", ""), ("shared", ";Abort_Across_GPUs=true")):
+        s = HostSolver(tree, "Num_Of_GPUs=2;Abort_RANSAC_by_Good_Sol=true;Num_Of_RANSAC_Iterations=4000" + ov)
+        s.round(fetch=False)
+        secs = [s.round(fetch=False)["seconds"] for _ in range(3)]
+        r = s.round(fetch=False)
+        s.close()
+        assert r["pose_found"] == 1 and r["best"][0] == 1 and r["best"][2] >= 4600 and r["best"][3] >= 4600, (key, r["best"][:5])
+        if key == "per_gpu":
+            assert r["best"][1] == 104          # (with the shared flag whichever GPU is first wins: hypothesis 0 on GPU 0 or 2003 on GPU 1)
+        assert np.all(r["residuals"] < 0.1)     # either way it is the ground-truth pose
+        out[key] = (min(secs), int(r["totals"][0]))
+    print("abort round, 4000 hypotheses on 2 GPUs: per-GPU flags %.2f ms (%d converged), shared flag %.2f ms (%d converged)"
+          % (out["per_gpu"][0] * 1e3, out["per_gpu"][1], out["shared"][0] * 1e3, out["shared"][1]))
+    assert out["shared"][0] <= out["per_gpu"][0] * 1.05          # never slower; faster whenever the second shard's first hit comes later
+    assert out["shared"][1] <= out["per_gpu"][1]                 # and less work was done
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def test_against_reference_gpu_kernels(problem, ransac0, default_round):
     """Second oracle: the reference's own GPU-HC++ kernels, compiled unmodified for sm_100a.  They use a different LU

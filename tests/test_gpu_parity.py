@@ -244,3 +244,44 @@ def test_split_long_paths_gives_identical_results(problem, ransac0, prune):
         assert np.array_equal(cv, cv0) and np.array_equal(inf, inf0), cut
         assert np.array_equal(st, st0), cut
         assert _bit_equal(tr, tr0), cut
+
+
+def test_early_abort_flag_crosses_gpus(problem, oracle, ransac0):
+    """hcb200_track_abort_peers: GPU 1 is given edgels no pose can match, so on its own it tracks its whole shard; with GPU 0 as a peer in the same
+    round it stops as soon as GPU 0's first passing path raises its flag through the NVLink peer mapping.  What GPU 1 did finish is its no-abort
+    result, bit for bit; its own record says it found nothing."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    H = 100
+    picked = hc.sample_hypotheses(0, H, ransac0["locations"].shape[0])
+    target, diff = hc.target_params_from_picks(picked, ransac0["locations"], ransac0["tangents"], problem["start_params"])
+    a = hc.Tracker(device="cuda:0", problem=problem, stats=True)
+    b = hc.Tracker(device="cuda:1", problem=problem, stats=True)
+    a.set_edgels(ransac0["locations"], ransac0["K"])
+    rng = np.random.RandomState(5)
+    b.set_edgels((rng.rand(*ransac0["locations"].shape) * 0.4 - 0.2).astype(np.float32), ransac0["K"])      # nothing reprojects within 2 px
+    a.upload_params(target, diff)
+    b.upload_params(target, diff)
+    b.track(H, prune=True)
+    tr_full, cv_full, inf_full, st_full = b.results(H)
+    # GPU 1 alone: no hit, the whole shard is tracked
+    b.track_abort(H, prune=True)
+    tr1, cv1, inf1, st1 = b.results(H)
+    assert int(b.d_found.cpu()[0]) == 0 and np.array_equal(cv1, cv_full) and ((st1[:, 3] >> 16) != 4).all()
+    # the same round with GPU 0 as a peer: both stop on GPU 0's hit
+    a.reset_abort(H); b.reset_abort(H)
+    torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+    b.track_abort(H, prune=True, peers=[a], reset=False)
+    a.track_abort(H, prune=True, peers=[b], reset=False)
+    tr_a, cv_a, inf_a, st_a = a.results(H)
+    tr_b, cv_b, inf_b, st_b = b.results(H)
+    assert int(a.d_found.cpu()[0]) == 1 and int(b.d_found.cpu()[0]) == 1
+    best_a, best_b = a.d_best.cpu().numpy(), b.d_best.cpu().numpy()
+    assert best_a[0] == 1 and best_a[1] == 104 and best_b[0] == 0          # GPU 0 found track 104 of hypothesis 0; GPU 1 found nothing itself
+    assert (b.d_found_index[:H * 312].cpu().numpy() == -1).all()
+    cut = (st_b[:, 3] >> 16) == 4                                           # skipped or stopped by the flag
+    assert cut.sum() > 20000, int(cut.sum())                                # GPU 1 did NOT track its whole shard this time
+    ran = ~cut
+    assert np.array_equal(cv_b[ran], cv_full[ran]) and np.array_equal(inf_b[ran], inf_full[ran])
+    assert _bit_equal(tr_b[ran][:, :30], tr_full[ran][:, :30])

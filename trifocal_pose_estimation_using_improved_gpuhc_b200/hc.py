@@ -27,7 +27,7 @@ _lib = None
 ABI_SYMBOLS = ("hcb200_workspace_bytes", "hcb200_abi_version", "hcb200_track", "hcb200_track_abort",
                "hcb200_build_target_params", "hcb200_score_tracks", "hcb200_refine_tracks", "hcb200_kernel_info", "hcb200_ffma_probe",
                "hcb200_error_string", "hcb200_make_pose_record", "hcb200_reduce_pose_records", "hcb200_count_solutions", "hcb200_problem_info",
-               "hcb200_workspace_bytes_for")
+               "hcb200_workspace_bytes_for", "hcb200_track_abort_peers", "hcb200_enable_peer_access")
 
 
 class HCB200Error(RuntimeError):
@@ -55,6 +55,10 @@ def load_library(path=None):
     lib.hcb200_track.argtypes = [vp, i32, i32, i32, i32, u32] + [vp] * 9
     lib.hcb200_track_abort.restype = i32
     lib.hcb200_track_abort.argtypes = [vp, i32, i32, i32, i32, i32, u32] + [vp] * 14
+    lib.hcb200_track_abort_peers.restype = i32
+    lib.hcb200_track_abort_peers.argtypes = [vp, i32, i32, i32, i32, i32, u32] + [vp] * 14 + [ctypes.POINTER(vp), i32]
+    lib.hcb200_enable_peer_access.restype = i32
+    lib.hcb200_enable_peer_access.argtypes = [i32, i32]
     lib.hcb200_build_target_params.restype = i32
     lib.hcb200_build_target_params.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp]
     lib.hcb200_kernel_info.restype = i32
@@ -234,19 +238,29 @@ class Tracker:
         _check(rc, "hcb200_track")
         self.launches += 1
 
-    def track_abort(self, n_hyp, prune=True):
-        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
-        n_paths = n_hyp * NUM_TRACKS
+    def reset_abort(self, n_hyp):
+        """Clear the early-abort flag and the found indices (the caller's job in the reference too, GPU_HC_Solver.cpp:321-324)."""
         self.d_found.zero_()
-        self.d_found_index[:n_paths].fill_(-1)
+        self.d_found_index[:n_hyp * NUM_TRACKS].fill_(-1)
+
+    def track_abort(self, n_hyp, prune=True, peers=None, reset=True):
+        """Early-abort launch.  peers: Trackers on OTHER GPUs of this process taking part in the same round — the first passing path raises their
+        flags too (hcb200_track_abort_peers, NVLink peer stores); every participant must then be reset (reset_abort) before the first launch of
+        the round, so pass reset=False here."""
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        if reset:
+            self.reset_abort(n_hyp)
+        args = [self._stream(), n_hyp, self.n_edgels, self.max_steps, self.max_corr, self.dt_inc, FLAG_PRUNE_PATHS if prune else 0,
+                p(self.d_start_sols), p(self.d_start_params), p(self.d_target), p(self.d_diff), p(self.d_edgels), p(self.d_K),
+                p(self.d_tracks), p(self.d_conv), p(self.d_inf), p(self.d_found), p(self.d_found_index), p(self.d_best), p(self.d_stats), p(self.d_ws)]
         with self.torch.cuda.device(self.device):
-            rc = self.lib.hcb200_track_abort(self._stream(), n_hyp, self.n_edgels, self.max_steps, self.max_corr, self.dt_inc,
-                                             FLAG_PRUNE_PATHS if prune else 0,
-                                             p(self.d_start_sols), p(self.d_start_params), p(self.d_target), p(self.d_diff),
-                                             p(self.d_edgels), p(self.d_K),
-                                             p(self.d_tracks), p(self.d_conv), p(self.d_inf),
-                                             p(self.d_found), p(self.d_found_index), p(self.d_best),
-                                             p(self.d_stats), p(self.d_ws))
+            if peers:
+                for q in peers:
+                    _check(self.lib.hcb200_enable_peer_access(self.device.index, q.device.index), "hcb200_enable_peer_access")
+                arr = (ctypes.c_void_p * len(peers))(*[q.d_found.data_ptr() for q in peers])
+                rc = self.lib.hcb200_track_abort_peers(*args, arr, len(peers))
+            else:
+                rc = self.lib.hcb200_track_abort(*args)
         _check(rc, "hcb200_track_abort")
         self.launches += 2
 

@@ -62,6 +62,7 @@ GPU_HC_Solver::GPU_HC_Solver(YAML::Node cfg) : Problem_Setting_YAML_File(cfg)
   refine_iterations               = cfg.as_or<int>("Refine_Iterations", 0);
   device_statistics               = cfg.as_or<bool>("Device_Statistics", true);
   split_long_paths                = cfg.as_or<bool>("Split_Long_Paths", true);
+  abort_across_gpus               = cfg.as_or<bool>("Abort_Across_GPUs", false);
   // Lazy_Results: auto (default) | true | false.  When statistics and scoring run on the GPU the host needs 12 bytes per hypothesis and one
   // 128-byte record per GPU; the 248 bytes per path of end points are then copied back only when somebody asks for them (Track_Sols(),
   // Sol_Converge(), Sol_Infinity(), hcb200_solver_copy_results).  auto = lazy from 2048 hypotheses up.
@@ -287,6 +288,13 @@ void GPU_HC_Solver::Set_RANSAC_Abort_Arrays()
     HC_CUDA(cudaMalloc((void**)&d.d_found_index, (paths ? paths : 1) * sizeof(int)));
     HC_CUDA(cudaMalloc((void**)&d.d_best, sizeof(hcb200_best_record)));
   }
+  if (abort_across_gpus && Num_Of_GPUs > 1) {             // every GPU will store into every other GPU's flag (NVLink peer mappings)
+    for (int g = 0; g < Num_Of_GPUs; g++)
+      for (int q = 0; q < Num_Of_GPUs; q++) {
+        const int rc = hcb200_enable_peer_access(shard[g].device, shard[q].device);
+        if (rc != 0) { std::fprintf(stderr, "[ERROR] Abort_Across_GPUs: GPU %d cannot reach GPU %d: %s\n", g, q, hcb200_error_string(rc)); std::exit(2); }
+      }
+  }
   abort_arrays_allocated = true;
 }
 
@@ -358,7 +366,16 @@ void GPU_HC_Solver::Solve_by_GPU_HC()
     HC_CUDA(cudaEventRecord((cudaEvent_t)d.ev_start, (cudaStream_t)d.stream));
     int rc;
     const unsigned flags = prune_flag | ((split_long_paths && sub_RANSAC_iters[g] <= HCB200_SPLIT_MAX_HYPOTHESES) ? HCB200_FLAG_SPLIT_LONG_PATHS : 0u);
-    if (Abort_RANSAC_by_Good_Sol)
+    if (Abort_RANSAC_by_Good_Sol && abort_across_gpus && Num_Of_GPUs > 1) {
+      uint8_t* peers[MAX_NUM_OF_GPUS];
+      int n_peers = 0;
+      for (int q = 0; q < Num_Of_GPUs; q++)
+        if (q != g && sub_RANSAC_iters[q]) peers[n_peers++] = shard[q].d_found;
+      rc = hcb200_track_abort_peers(d.stream, sub_RANSAC_iters[g], Num_Of_Triplet_Edgels, GPUHC_Max_Steps, GPUHC_Max_Correction_Steps,
+                                    GPUHC_delta_t_incremental_steps, flags, d.d_start_sols, d.d_start_params, d.d_target, d.d_diff,
+                                    d.d_edgels, d.d_K, d.d_tracks, d.d_conv, d.d_inf, d.d_found, d.d_found_index, d.d_best, nullptr, d.d_ws,
+                                    peers, n_peers);
+    } else if (Abort_RANSAC_by_Good_Sol)
       rc = hcb200_track_abort(d.stream, sub_RANSAC_iters[g], Num_Of_Triplet_Edgels, GPUHC_Max_Steps, GPUHC_Max_Correction_Steps,
                               GPUHC_delta_t_incremental_steps, flags, d.d_start_sols, d.d_start_params, d.d_target, d.d_diff,
                               d.d_edgels, d.d_K, d.d_tracks, d.d_conv, d.d_inf, d.d_found, d.d_found_index, d.d_best, nullptr, d.d_ws);

@@ -146,6 +146,9 @@ private:
   // Long paths are parked at 4/5 of the step cap and finished by idle warps (HCB200_FLAG_SPLIT_LONG_PATHS; YAML key Split_Long_Paths,
   // default true): same results, the default round ends 3.6 % sooner.  Costs 20 bytes of device workspace per path.
   bool split_long_paths = true;
+  // Early abort across GPUs (YAML key Abort_Across_GPUs, default false = the reference's per-GPU flag, GPU_HC_Solver.cpp:329,402): the first GPU
+  // that finds a pose raises the other GPUs' flags through NVLink peer stores (hcb200_track_abort_peers), so the round ends when ANY GPU has one.
+  bool abort_across_gpus = false;
   bool result_stacks_allocated = false;
   bool lazy_results = false, results_on_host = false;
   hcb200::complex32 h_selected_track[32];
