@@ -159,6 +159,28 @@ def test_libraries_export_problem_info():
             getattr(lib, sym)
 
 
+def test_hc_main_refuses_what_it_cannot_run(tmp_path):
+    """Host logic of `hc-main -p <problem>` that needs no GPU: a folder nobody compiled is refused with the build command; a compiled problem
+    without a CUDA device is a loud error, not a CPU fallback."""
+    import shutil
+    import torch
+    exe = os.path.join(PKG, "lib", "hc-main")
+    name = PROBLEMS[0]
+    root = str(tmp_path)
+    os.makedirs(os.path.join(root, "Output_Write_Files"))
+    shutil.copytree(_pdir(name), os.path.join(root, "problems", name))
+    shutil.copytree(_pdir(name), os.path.join(root, "problems", "uncompiled"))
+    y = os.path.join(root, "problems", "uncompiled", "gpuhc_settings.yaml")
+    text = open(y).read().replace("problem_name: " + name, "problem_name: uncompiled")
+    open(y, "w").write(text)
+    out = subprocess.run([exe, "-p", "uncompiled", "-d", root], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "make problem PROBLEM_DIR=problems/uncompiled" in out.stdout + out.stderr
+    if not torch.cuda.is_available() and os.path.exists(os.path.join(PKG, "lib", "libhcb200_%s.so" % name)):
+        out = subprocess.run([exe, "-p", name, "-d", root], capture_output=True, text=True, timeout=60)
+        assert out.returncode != 0 and "no CUDA device" in out.stdout + out.stderr
+        assert not os.path.exists(os.path.join(root, "Output_Write_Files", "GPU_Sols_Statistics.txt"))
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU
 
