@@ -136,21 +136,10 @@ def write_folder(path):
             for row in arr.reshape(-1, N):
                 f.write("\t".join(str(int(v)) for v in row) + "\t\n")
     with open(os.path.join(path, "gpuhc_settings.yaml"), "w") as f:
-        f.write("""%%YAML:1.0
+        f.write("""# Settings of the synthetic minimal problem "%s" (written by tools/make_synthetic_problem.py).
+# Key names are the ones the reference's readers look up (CPU_HC_Solver.cpp:34-60, GPU_HC_Solver.cpp:36-70); values describe THIS system.
 
-#> Problem Name (must be the same as the problem folder name)
-problem_name: %s
-problem_print_out_name: %s (synthetic problem for the problem compiler)
-
-#> GPU Settings
-Num_Of_GPUs:  1
-
-#> GPU-HC Settings
-GPUHC_Max_Steps: 80
-GPUHC_Max_Correction_Steps: 3
-GPUHC_Num_Of_Steps_to_Increase_Delta_t: 4
-
-#> Problem spec
+# sizes of the polynomial system and of its evaluation-index tables
 Num_Of_Vars: %d
 Num_Of_Params: %d
 Num_Of_Tracks: %d
@@ -158,21 +147,25 @@ dHdx_Max_Terms: %d
 dHdx_Max_Parts: 5
 dHdt_Max_Terms: %d
 dHdt_Max_Parts: 6
-Max_Order_Of_T: 2
-Num_Of_Coeffs_From_Params: 0
-#> (extension of this repository) leading unknowns that must become positive for a path to be kept: the reference's GPU kernels
-#> hard-code 8 depths for the trifocal problem (…TrunPaths.cu:148-154)
+# leading unknowns that must become positive for a path to be kept (an extension of this repository: the reference's GPU kernels hard-code
+# 8 depths for the trifocal problem, TrunPaths.cu:148-154); 0 switches pruning off
 Num_Of_Depth_Vars: %d
 
-#> Algorithmic Setting
-Abort_RANSAC_by_Good_Sol: false
+# identity
+problem_name: %s
+problem_print_out_name: %s (synthetic problem for the problem compiler)
 
-#> RANSAC data
+# path tracker: step cap, Newton iterations per step, successes before the step doubles
+GPUHC_Max_Steps: 80
+GPUHC_Max_Correction_Steps: 3
+GPUHC_Num_Of_Steps_to_Increase_Delta_t: 4
+
+# keys the reference's solver objects insist on although a synthetic problem has no RANSAC data
+Num_Of_GPUs: 1
+Num_Of_Cores: 4
 RANSAC_Dataset: Synthetic
-
-#> CPU-HC Settings
-Num_Of_Cores:  4
-""" % (NAME, NAME.replace("_", " "), N, NP, 1 << N, hx.shape[1], ht.shape[0], SIZES[NAME][2]))
+Abort_RANSAC_by_Good_Sol: false
+""" % (NAME, N, NP, 1 << N, hx.shape[1], ht.shape[0], SIZES[NAME][2], NAME, NAME.replace("_", " ")))
     return hx, ht, sp, sols
 
 
