@@ -285,3 +285,28 @@ def test_early_abort_flag_crosses_gpus(problem, oracle, ransac0):
     ran = ~cut
     assert np.array_equal(cv_b[ran], cv_full[ran]) and np.array_equal(inf_b[ran], inf_full[ran])
     assert _bit_equal(tr_b[ran][:, :30], tr_full[ran][:, :30])
+
+
+def test_split_workspace_is_not_overrun(problem, ransac0):
+    """The split kernel writes a list entry and 16 bytes of state per parked path behind the 256-byte header: with EVERY path parked (step 1) the
+    bytes beyond hcb200_workspace_bytes_for(H) must stay untouched, and so must the tail of the result arrays."""
+    import torch
+    H = 40
+    picked = hc.sample_hypotheses(9, H, ransac0["locations"].shape[0])
+    target, diff = hc.target_params_from_picks(picked, ransac0["locations"], ransac0["tangents"], problem["start_params"])
+    trk = hc.Tracker(problem=problem, stats=True, split=True)
+    trk.upload_params(target, diff)
+    need = int(trk.lib.hcb200_workspace_bytes_for(H))
+    ws = torch.full((need + 4096,), 0xA5, dtype=torch.uint8, device=trk.device)
+    trk.d_ws = ws
+    pad = 64
+    tracks = torch.full((H * 312 * 31 * 2 + pad,), 7.0, dtype=torch.float32, device=trk.device)
+    trk.d_tracks = tracks[:H * 312 * 31 * 2].view(H * 312, 31, 2)
+    for cut in (1, 64):
+        trk.suspend_step = cut
+        trk.track(H, prune=True)
+        torch.cuda.synchronize()
+        assert bool((ws[need:] == 0xA5).all()), cut
+        assert bool((tracks[H * 312 * 31 * 2:] == 7.0).all()), cut
+    parked = ws[256:256 + H * 312 * 4].view(torch.int32)
+    assert int((parked != 0).sum()) > 1000          # the list was really used
