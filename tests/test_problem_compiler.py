@@ -222,6 +222,18 @@ def test_gpu_tracker_of_a_compiled_problem_is_bit_identical_to_the_oracle(name):
         xo, sd, sx = orc.refine(tgt[0], x1, iters=2)
         assert np.array_equal(np.ascontiguousarray(xo[:n]).view(np.uint64), np.ascontiguousarray(tr2[path, :n]).view(np.uint64))
         assert np.float32(sd) == sums[path, 0] and np.float32(sx) == sums[path, 1]
+    # nothing is written beyond the problem's (smaller) arrays: guard bytes behind tracks, flags and workspace survive a launch
+    P = H * T
+    g_tr = torch.full((P * (n + 1) * 2 + 64,), 7.0, dtype=torch.float32, device=trk.device)
+    g_cv = torch.full((P + 64,), 0x5A, dtype=torch.uint8, device=trk.device)
+    g_inf = torch.full((P + 64,), 0x5A, dtype=torch.uint8, device=trk.device)
+    need = int(trk.lib.hcb200_workspace_bytes_for(H))
+    g_ws = torch.full((need + 1024,), 0xA5, dtype=torch.uint8, device=trk.device)
+    trk.d_tracks, trk.d_conv, trk.d_inf, trk.d_ws = g_tr[:P * (n + 1) * 2].view(P, n + 1, 2), g_cv[:P], g_inf[:P], g_ws
+    trk.track(H, prune=False)
+    torch.cuda.synchronize()
+    assert bool((g_tr[P * (n + 1) * 2:] == 7.0).all()) and bool((g_cv[P:] == 0x5A).all()) and bool((g_inf[P:] == 0x5A).all()) and bool((g_ws[need:] == 0xA5).all())
+    assert np.array_equal(trk.d_conv.cpu().numpy(), cv)
     # the entry points that know what trifocal unknowns MEAN refuse to run on another problem
     rc = trk.lib.hcb200_track_abort(None, 1, 10, 80, 3, 4, 0, *([None] * 14))
     assert rc != 0 and b"not supported" in trk.lib.hcb200_error_string(rc).lower()
