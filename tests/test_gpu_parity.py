@@ -310,3 +310,24 @@ def test_split_workspace_is_not_overrun(problem, ransac0):
         assert bool((tracks[H * 312 * 31 * 2:] == 7.0).all()), cut
     parked = ws[256:256 + H * 312 * 4].view(torch.int32)
     assert int((parked != 0).sum()) > 1000          # the list was really used
+
+
+def test_repeated_launches_are_identical(problem, ransac0):
+    """No race: warps hand paths to each other through atomics, shared-memory rows and (split mode) parked state, in an order that differs from
+    launch to launch — the results must not."""
+    H = 100
+    picked = hc.sample_hypotheses(0, H, ransac0["locations"].shape[0])
+    target, diff = hc.target_params_from_picks(picked, ransac0["locations"], ransac0["tangents"], problem["start_params"])
+    for split in (True, False):
+        trk = hc.Tracker(problem=problem, stats=True, split=split)
+        trk.upload_params(target, diff)
+        first = None
+        for rep in range(8):
+            trk.d_tracks.zero_()
+            trk.track(H, prune=True)
+            out = trk.results(H)
+            if first is None:
+                first = out
+            else:
+                assert np.array_equal(out[1], first[1]) and np.array_equal(out[2], first[2]) and np.array_equal(out[3], first[3]), (split, rep)
+                assert _bit_equal(out[0], first[0]), (split, rep)
