@@ -160,7 +160,29 @@ def level_schedule(hx_terms, K1, segments, seg_cols):
         shared = [c for c in range(K1, N) if need[c]]
         levels.append(here)
         first_shared.append(min(shared) if shared else N)
+    level_schedule.group_patterns = [(l, g, c, part, u) for (l, g, c, part, u) in groups]      # kept for store_limits()
     return levels, level_of_col, first_shared
+
+
+def store_limits(K1, nsp, nslot, lane_of_row):
+    """Per super-step T and slot pair (t, t+1): one past the highest lane whose pivot group can hold a non-zero in that pair (sparse slots and
+    the right-hand side pair count as always needed).  A pivot lane at or above the limit need not store the pair — its group's buffer keeps
+    the zeros it was initialised with — which matters because a 128-bit store costs one shared-memory wavefront per quarter-warp that holds a
+    storing lane."""
+    lim = [[32] * (nslot // 2) for _ in range(nsp)]
+    for T in range(nsp):
+        for pr in range(nslot // 2):
+            t = 2 * pr
+            if t < nsp:
+                continue                                  # pairs that hold sparse slots: keep unconditional
+            top = 0
+            for (l, g, c, part, u) in level_schedule.group_patterns:
+                if l != T:
+                    continue
+                if u[K1 + (t - nsp)] or u[K1 + (t + 1 - nsp)]:
+                    top = max(top, 1 + max(lane_of_row[r] for r in part))
+            lim[T][pr] = top if top > 0 else 32           # (untouched pairs are not stored at all: the limit is irrelevant)
+    return lim
 
 
 def column_classes(hx_terms):
@@ -344,6 +366,7 @@ def build():
     lane_of_row = [row_of_lane.index(r) for r in range(N)]
     nsp = len(levels)
     nd = N - K1
+    sp_store_limit = store_limits(K1, nsp, nsp + nd, lane_of_row) if nsp else []
     # per lane and level: the private column the lane's row meets there (or None), the lanes of its group (6-bit mask relative
     # to the segment's first lane) and the group's index within the segment (selects the pivot-row buffer)
     col_at = [[None] * nsp for _ in range(WARP)]
@@ -495,7 +518,7 @@ def build():
     return dict(hx_terms=hx_terms, h_terms=h_terms, cq_list=cq_list, dq_list=dq_list, classes=classes,
                 col_class=col_class, hx_slots=hx_slots, h_slots=h_slots, ht_slots=ht_slots,
                 K1=K1, segments=segments, seg_cols=seg_cols, row_of_lane=row_of_lane, lane_of_row=lane_of_row,
-                nsp=nsp, nd=nd, nslot=nslot, sp_first_shared=sp_first_shared, levels=levels, level_of_col=level_of_col,
+                nsp=nsp, nd=nd, nslot=nslot, sp_first_shared=sp_first_shared, sp_store_limit=sp_store_limit, levels=levels, level_of_col=level_of_col,
                 col_at=col_at, grp_mask=grp_mask, grp_sub=grp_sub, max_sub=max_sub, scatter=scatter, sel_of_lane=sel_of_lane, nz_of_lane=nz_of_lane, n_sel=n_sel,
                 pairs=pair_by_pos, triples=tri_by_pos, XP_PAIR0=XP_PAIR0, XP_TRI0=XP_TRI0, XP_TOTAL=XP_TOTAL,
                 layout_cost=layout_cost)
@@ -639,6 +662,8 @@ def emit(g, path):
     for t, (ca, cb, sb) in enumerate(g["scatter"]):
         w("  X(%d, %d, %d, %d) \\" % (t, ca, cb, sb))
     w("")
+    w("// per super-step and slot pair: pivot lanes at or above this lane never hold a non-zero there and skip the store (32: everybody stores)")
+    w("#define HCG_SP_STORE_LIMIT_INIT { " + ", ".join("{" + ",".join(str(v) for v in row) + "}" for row in (g["sp_store_limit"] or [[32] * (g["nslot"] // 2)])) + " }")
     w("// problem identity: the kernel takes every size from this header (codegen/gen_eval.py --problem-dir compiles another problem)")
     w("#define HCG_PROBLEM_NAME \"%s\"" % SPEC["name"])
     w("#define HCG_TRACKS %d        /* homotopy paths per hypothesis (Num_Of_Tracks) */" % SPEC["n_tracks"])
