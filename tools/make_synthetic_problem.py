@@ -13,6 +13,10 @@ all six pivot steps warp-wide (the compiler's fallback):
 
     f_i = x_i^2 - p_i^2 + p_6 x_i (sum over j != i of x_j)
 
+mixed_12x12 (12 unknowns, 14 parameters, 64 paths) — six quadrics and six equations that are linear in their own unknown, two 6-row blocks:
+
+    f_i = x_i^2 - p_i^2 + p_12 x_{i+1} x_{i+6}   (i < 6)        f_i = x_i - p_i + p_13 x_{i-6} x_{i+1}   (i >= 6)
+
 Start parameters: p_0..p_7 = a_i (random complex, fixed seed), p_8 = p_9 = 0  ->  the start system decouples into x_i^2 = a_i^2 and has the
 2^8 = 256 regular solutions x_i = +-a_i: those are the start solutions (Num_Of_Tracks = 256).  Target parameters are real, like the
 reference's (they come from image measurements there): every hypothesis draws p_0..p_7 in [0.6, 1.4] and the couplings p_8, p_9 in
@@ -28,8 +32,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NAME = "coupled_quadrics_8x8"
-NAMES = ("coupled_quadrics_8x8", "dense_quadrics_6x6")
-SIZES = {"coupled_quadrics_8x8": (8, 10, 2), "dense_quadrics_6x6": (6, 7, 0)}      # unknowns, parameters, depth unknowns
+NAMES = ("coupled_quadrics_8x8", "dense_quadrics_6x6", "mixed_12x12")
+SIZES = {"coupled_quadrics_8x8": (8, 10, 2), "dense_quadrics_6x6": (6, 7, 0), "mixed_12x12": (12, 14, 3)}      # unknowns, parameters, depth unknowns
+N_SQUARES = {"coupled_quadrics_8x8": 8, "dense_quadrics_6x6": 6, "mixed_12x12": 6}      # equations that are quadratic in their own unknown: 2^k start solutions
 N, NP = 8, 10
 X_PAD, P_PAD = N, NP
 
@@ -52,8 +57,12 @@ def system():
                  (1, 9, P_PAD, [(i + 2) % N])]
             if i in (0, 4):
                 t.append((1, 8, 9, [(i + 5) % N, (i + 6) % N, (i + 7) % N]))
-        else:
+        elif NAME == "dense_quadrics_6x6":
             t = [(1, P_PAD, P_PAD, [i, i]), (-1, i, i, [])] + [(1, N, P_PAD, sorted([i, j])) for j in range(N) if j != i]
+        elif i < 6:
+            t = [(1, P_PAD, P_PAD, [i, i]), (-1, i, i, []), (1, 12, P_PAD, sorted([(i + 1) % N, (i + 6) % N]))]
+        else:
+            t = [(1, P_PAD, P_PAD, [i]), (-1, i, P_PAD, []), (1, 13, P_PAD, sorted([i - 6, (i + 1) % N]))]
         eqs.append(t)
     return eqs
 
@@ -96,10 +105,11 @@ def start_data(seed=20241):
     a = (rng.uniform(0.7, 1.3, N) * np.exp(1j * rng.uniform(-np.pi, np.pi, N))).astype(np.complex64)
     sp = np.zeros(NP, np.complex64)
     sp[:N] = a
-    sols = np.empty((1 << N, N), np.complex64)
-    for k in range(1 << N):
+    k2 = N_SQUARES[NAME]
+    sols = np.empty((1 << k2, N), np.complex64)
+    for k in range(1 << k2):
         for i in range(N):
-            sols[k, i] = a[i] if not (k >> i) & 1 else -a[i]
+            sols[k, i] = -a[i] if (i < k2 and (k >> i) & 1) else a[i]
     return sp, sols
 
 
@@ -108,7 +118,7 @@ def target_params(n_hyp, seed=1):
     rng = np.random.RandomState(seed)
     t = np.zeros((n_hyp, NP + 1), np.complex64)
     t[:, :N] = rng.uniform(0.6, 1.4, (n_hyp, N)).astype(np.float32)
-    lim = 0.45 if NAME == "coupled_quadrics_8x8" else 0.3
+    lim = {"coupled_quadrics_8x8": 0.45, "dense_quadrics_6x6": 0.3, "mixed_12x12": 0.4}[NAME]
     for k in range(N, NP):                                   # the coupling parameters (0 in the start system)
         t[:, k] = rng.uniform(-lim, lim, n_hyp).astype(np.float32)
     t[:, NP] = 1.0
@@ -165,7 +175,7 @@ Num_Of_GPUs: 1
 Num_Of_Cores: 4
 RANSAC_Dataset: Synthetic
 Abort_RANSAC_by_Good_Sol: false
-""" % (NAME, N, NP, 1 << N, hx.shape[1], ht.shape[0], SIZES[NAME][2], NAME, NAME.replace("_", " ")))
+""" % (NAME, N, NP, 1 << N_SQUARES[NAME], hx.shape[1], ht.shape[0], SIZES[NAME][2], NAME, NAME.replace("_", " ")))
     return hx, ht, sp, sols
 
 
